@@ -1,0 +1,552 @@
+// bbfft_kernels.cuh -- hand-written sm_100a device templates for the double-batched small FFT.
+//
+// This single header is the whole device side of the library.  It is
+//   * compiled by NVRTC at plan creation (the host embeds this text; see jit.cpp),
+//   * compiled by nvcc for the built-in / AOT kernel bundles (same text, same stubs),
+//   * compiled by g++ against tests/emu/cuda_emu.hpp (macro BBFFT_EMU) so that every index
+//     map can be checked on a CPU-only box.  That emulation is test infrastructure only.
+//
+// A kernel is instantiated by a small generated "stub" (planner.cpp: emit_stub) that defines a
+// traits struct `C` (all compile-time plan parameters) and one
+//     extern "C" __global__ void <identifier>(bbk::args a) { bbk::fft1d<C>(a); }
+//
+// What replaces what in the reference (intel/double-batched-fft-library):
+//   reg_fft / bfly        <- src/base/mixed_radix_fft.cpp:215-254 (in-register FFT), :78-126 (pair trick)
+//   fft1d, L == 1         <- src/base/generator/sbfft_gen.cpp:30-134   ("small batch" kernel)
+//   fft1d, L >= 2         <- src/base/generator/f2fft_gen.cpp:46-183   ("factor2 slm" kernel)
+//   real pre/post passes  <- sbfft_gen.cpp:162-351, f2fft_gen.cpp:228-502
+//   C::ld / C::st hooks   <- src/base/generator/tensor_accessor.cpp:34-55 (callback_accessor)
+// The algorithm is NOT a translation: stages are radix-2..16 Stockham-style passes that work in
+// place in shared memory (digit reversal folded into the final store), threads are laid out so
+// that the M batch index runs along the lanes of a warp (coalesced 128-byte rows, conflict-free
+// shared memory without padding), and twiddles between stages come from a small L1-resident
+// table.
+//
+// Tensor layout (reference include/bbfft/configuration.hpp:162-179): element (m, n, k) of the
+// M x N x K tensor lives at offset m + n*s1 + k*s2 counted in elements of the tensor's own type.
+#ifndef BBFFT_KERNELS_CUH
+#define BBFFT_KERNELS_CUH
+
+#ifdef BBFFT_EMU
+#define BBK_DEV inline
+#define BBK_HD inline
+#define BBK_CE constexpr
+#define BBK_RESTRICT __restrict__
+#define BBK_GLOBAL
+#define BBK_LAUNCH_BOUNDS(t, b)
+#else
+#define BBK_DEV __device__ __forceinline__
+#define BBK_HD __host__ __device__ __forceinline__
+#define BBK_CE __host__ __device__ constexpr
+#define BBK_GLOBAL __global__
+#define BBK_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define BBK_RESTRICT __restrict__
+#endif
+
+namespace bbk {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+// transform modes (C::MODE)
+enum : int {
+    C2C = 0,
+    R2C_HALF = 1,   // even N: half-length complex FFT + fused post-twiddle
+    C2R_HALF = 2,   // even N: fused pre-twiddle + half-length complex FFT
+    R2C_DOUBLE = 3, // odd N: two real rows (k, k+1) through one complex FFT
+    C2R_DOUBLE = 4
+};
+
+// Kernel arguments.  One signature for every kernel; strides are only read when the stub was
+// generated with run-time strides (the default is compile-time strides like the reference,
+// whose identifiers carry them: src/base/generator/small_batch_fft.cpp:60-80).
+struct args {
+    const void *in;
+    void *out;
+    const void *tw; // inter-stage twiddle table (+ real post/pre table), element type cx<real_t>
+    u64 K;          // number of k slices handled by this launch
+    u64 M;
+    i64 is1, is2, os1, os2;
+};
+
+template <class T> struct alignas(2 * sizeof(T)) cx {
+    T x, y;
+};
+
+template <class T> BBK_DEV cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
+template <class T> BBK_DEV cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
+template <class T> BBK_DEV cx<T> cmul(cx<T> a, cx<T> b) {
+    return cx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <class T> BBK_DEV cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
+// multiply by DIR*i  (= exp(DIR*i*pi/2))
+template <int DIR, class T> BBK_DEV cx<T> mul_i(cx<T> a) {
+    return DIR < 0 ? cx<T>{a.y, -a.x} : cx<T>{-a.y, a.x};
+}
+
+// read-only (L1-resident) load of a table entry
+#ifdef BBFFT_EMU
+template <class T> BBK_DEV cx<T> ldg_cx(const cx<T> *p) { return *p; }
+#else
+BBK_DEV cx<float> ldg_cx(const cx<float> *p) {
+    float2 r = __ldg(reinterpret_cast<const float2 *>(p));
+    return cx<float>{r.x, r.y};
+}
+BBK_DEV cx<double> ldg_cx(const cx<double> *p) {
+    double2 r = __ldg(reinterpret_cast<const double2 *>(p));
+    return cx<double>{r.x, r.y};
+}
+#endif
+
+template <int I> struct ic {
+    static constexpr int value = I;
+};
+template <int B, int E, class F> BBK_DEV void static_for(F &&f) {
+    if constexpr (B < E) {
+        f(ic<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// In-register FFTs.  `W` is a generated table type: W::n entries, W::c(k) = cos(2 pi k / n),
+// W::s(k) = sin(2 pi k / n), exactly rounded from long double on the host.  A transform of
+// length R (R | W::n) uses every (W::n / R)-th entry.
+// ------------------------------------------------------------------------------------------
+template <class T, class W, int R, int K, int DIR> BBK_DEV cx<T> twc() {
+    constexpr int idx = ((K % R) + R) % R * (W::n / R);
+    constexpr T c = T(W::c(idx));
+    constexpr T s = T(W::s(idx));
+    return cx<T>{c, DIR < 0 ? -s : s};
+}
+
+// multiply by the compile-time constant w_R^K with the trivial cases folded away
+template <class T, class W, int R, int K, int DIR> BBK_DEV cx<T> mul_w(cx<T> a) {
+    constexpr int k = ((K % R) + R) % R;
+    if constexpr (k == 0) {
+        return a;
+    } else if constexpr (4 * k == R) {
+        return mul_i<DIR>(a);
+    } else if constexpr (2 * k == R) {
+        return cx<T>{-a.x, -a.y};
+    } else if constexpr (4 * k == 3 * R) {
+        return mul_i<-DIR>(a);
+    } else if constexpr (8 * k == R || 8 * k == 3 * R || 8 * k == 5 * R || 8 * k == 7 * R) {
+        // (+-1 +- i)/sqrt(2): two adds and two multiplies
+        constexpr T h = T(0.70710678118654752440084436210484903928L);
+        constexpr int o = 8 * k / R; // 1,3,5,7
+        // w = (cr + i*ci*DIR)/sqrt2 with cr,ci in {+1,-1}
+        constexpr int cr = (o == 1 || o == 7) ? 1 : -1;
+        constexpr int ci0 = (o == 1 || o == 3) ? 1 : -1;
+        constexpr int ci = DIR < 0 ? -ci0 : ci0;
+        // (a.x + i a.y)(cr + i ci) = (cr a.x - ci a.y) + i (ci a.x + cr a.y)
+        T re = (cr > 0 ? a.x : -a.x) - (ci > 0 ? a.y : -a.y);
+        T im = (ci > 0 ? a.x : -a.x) + (cr > 0 ? a.y : -a.y);
+        return cx<T>{re * h, im * h};
+    } else {
+        return cmul(a, twc<T, W, R, k, DIR>());
+    }
+}
+
+// Prime / small butterflies: natural order in, natural order out.
+template <class T, class W, int R, int DIR> struct bfly {
+    // generic odd prime: direct DFT with the conjugate-pair factoring
+    // (same arithmetic idea as the reference's pair_optimization_esum, mixed_radix_fft.cpp:78-126)
+    static BBK_DEV void run(cx<T> *v) {
+        static_assert(R % 2 == 1, "generic butterfly is for odd radices");
+        constexpr int H = (R - 1) / 2;
+        cx<T> s[H + 1], d[H + 1];
+        static_for<1, H + 1>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            s[j] = v[j] + v[R - j];
+            d[j] = v[j] - v[R - j];
+        });
+        cx<T> x0 = v[0];
+        cx<T> sum = x0;
+        static_for<1, H + 1>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            sum = sum + s[j];
+        });
+        v[0] = sum;
+        static_for<1, H + 1>([&](auto kk) {
+            constexpr int k = decltype(kk)::value;
+            cx<T> re = x0; // sum_j cos(jk) s_j
+            cx<T> im = cx<T>{T(0), T(0)}; // sum_j sin(jk) d_j
+            static_for<1, H + 1>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                constexpr int idx = (j * k) % R * (W::n / R);
+                constexpr T c = T(W::c(idx));
+                constexpr T sn = T(W::s(idx));
+                re.x += c * s[j].x;
+                re.y += c * s[j].y;
+                if constexpr (j == 1) {
+                    im.x = sn * d[j].x;
+                    im.y = sn * d[j].y;
+                } else {
+                    im.x += sn * d[j].x;
+                    im.y += sn * d[j].y;
+                }
+            });
+            cx<T> rot = mul_i<DIR>(im); // DIR * i * im
+            v[k] = re + rot;
+            v[R - k] = re - rot;
+        });
+    }
+};
+
+template <class T, class W, int DIR> struct bfly<T, W, 1, DIR> {
+    static BBK_DEV void run(cx<T> *) {}
+};
+template <class T, class W, int DIR> struct bfly<T, W, 2, DIR> {
+    static BBK_DEV void run(cx<T> *v) {
+        cx<T> a = v[0], b = v[1];
+        v[0] = a + b;
+        v[1] = a - b;
+    }
+};
+template <class T, class W, int DIR> struct bfly<T, W, 4, DIR> {
+    static BBK_DEV void run(cx<T> *v) {
+        cx<T> t0 = v[0] + v[2], t1 = v[0] - v[2];
+        cx<T> t2 = v[1] + v[3], t3 = mul_i<DIR>(v[1] - v[3]);
+        v[0] = t0 + t2;
+        v[1] = t1 + t3;
+        v[2] = t0 - t2;
+        v[3] = t1 - t3;
+    }
+};
+template <class T, class W, int DIR> struct bfly<T, W, 8, DIR> {
+    static BBK_DEV void run(cx<T> *v) {
+        constexpr T h = T(0.70710678118654752440084436210484903928L);
+        // first level: b_j = a_j + a_{j+4}, c_j = (a_j - a_{j+4}) w8^j
+        cx<T> b0 = v[0] + v[4], c0 = v[0] - v[4];
+        cx<T> b1 = v[1] + v[5], c1 = v[1] - v[5];
+        cx<T> b2 = v[2] + v[6], c2 = mul_i<DIR>(v[2] - v[6]);
+        cx<T> b3 = v[3] + v[7], c3 = v[3] - v[7];
+        // w8^1 = (1 + DIR i)/sqrt2 ; w8^3 = (-1 + DIR i)/sqrt2
+        cx<T> r1 = mul_i<DIR>(c1), r3 = mul_i<DIR>(c3);
+        c1 = cx<T>{(c1.x + r1.x) * h, (c1.y + r1.y) * h};
+        c3 = cx<T>{(r3.x - c3.x) * h, (r3.y - c3.y) * h};
+        // even outputs: radix-4 on b, odd outputs: radix-4 on c
+        cx<T> e0 = b0 + b2, e1 = b0 - b2, e2 = b1 + b3, e3 = mul_i<DIR>(b1 - b3);
+        cx<T> o0 = c0 + c2, o1 = c0 - c2, o2 = c1 + c3, o3 = mul_i<DIR>(c1 - c3);
+        v[0] = e0 + e2;
+        v[2] = e1 + e3;
+        v[4] = e0 - e2;
+        v[6] = e1 - e3;
+        v[1] = o0 + o2;
+        v[3] = o1 + o3;
+        v[5] = o0 - o2;
+        v[7] = o1 - o3;
+    }
+};
+
+BBK_CE int first_radix(int r) {
+    if (r % 8 == 0 && r != 16) return 8;
+    if (r % 4 == 0) return 4;
+    if (r % 2 == 0) return 2;
+    for (int p = 3; p * p <= r; p += 2) {
+        if (r % p == 0) return p;
+    }
+    return r;
+}
+
+// Composite in-register FFT of length R on v[0..R-1] (natural order in and out).
+template <class T, class W, int R, int DIR> struct reg_fft {
+    static BBK_DEV void run(cx<T> *v) {
+        constexpr int A = first_radix(R);
+        if constexpr (A == R) {
+            bfly<T, W, R, DIR>::run(v);
+        } else {
+            constexpr int B = R / A;
+            cx<T> y[R]; // y[q*B + n]
+            static_for<0, B>([&](auto nn) {
+                constexpr int n = decltype(nn)::value;
+                cx<T> u[A];
+                static_for<0, A>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    u[j] = v[n + B * j];
+                });
+                bfly<T, W, A, DIR>::run(u);
+                static_for<0, A>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    y[q * B + n] = mul_w<T, W, R, n * q, DIR>(u[q]);
+                });
+            });
+            static_for<0, A>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                reg_fft<T, W, B, DIR>::run(y + q * B);
+            });
+            static_for<0, A>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                static_for<0, B>([&](auto pp) {
+                    constexpr int p = decltype(pp)::value;
+                    v[q + A * p] = y[q * B + p];
+                });
+            });
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Plan traits contract (generated):
+//   real_t, N (complex FFT length run by the stages), NREAL (user-visible length for real
+//   modes), DIR, MODE, L (stages), radix(s), T (threads per transform), ML (batch lanes, the
+//   fastest thread index), BH (further batch entries per CTA), KLANES (batch lanes index k
+//   instead of m; only for M == 1), M, LOAD_STAGED / STORE_STAGED, smem layout LL / PADK /
+//   ROW, twiddle block offsets tw_off(s), WR<s> table types, is1()..os2() stride accessors and
+//   the ld/st hooks.
+// ------------------------------------------------------------------------------------------
+template <class C> struct geom {
+    static constexpr int B = C::ML * C::BH;          // transforms per CTA
+    static constexpr int THREADS = C::ML * C::T * C::BH;
+    static BBK_CE int ns(int s) {                 // N_s: sub-problem length entering stage s
+        int n = C::N;
+        for (int i = 0; i < s; ++i) n /= C::radix(i);
+        return n;
+    }
+    // padded position inside one transform's shared-memory row
+    static BBK_DEV int pad(int pos) {
+        if constexpr (C::PADK > 0) {
+            return pos + pos / C::PADK;
+        } else {
+            return pos;
+        }
+    }
+    // shared memory offset (in elements) of element `pos` of CTA-local transform b
+    static BBK_DEV int soff(int b, int pos) {
+        if constexpr (C::LL > 1) {
+            return (b % C::LL) + C::LL * pad(pos) + C::ROW * (b / C::LL);
+        } else {
+            return pad(pos) + C::ROW * b;
+        }
+    }
+};
+
+// digit reversal: position after the last in-place stage -> output bin
+template <class C> BBK_DEV int bin_of_sub(int u) {
+    // u = (((q0*R1 + q1)*R2 + q2) ... + q_{L-2}); returns q0 + R0*(q1 + R1*(q2 + ...))
+    int k = 0;
+    int rem = u;
+    // peel digits from the least significant (q_{L-2}) upwards
+    int digits[4] = {0, 0, 0, 0};
+    static_for<0, C::L - 1>([&](auto ii) {
+        constexpr int s = C::L - 2 - decltype(ii)::value;
+        digits[s] = rem % C::radix(s);
+        rem /= C::radix(s);
+    });
+    static_for<0, C::L - 1>([&](auto ii) {
+        constexpr int s = C::L - 2 - decltype(ii)::value;
+        k = k * C::radix(s) + digits[s];
+    });
+    return k;
+}
+// full digit reversal of a position 0..N-1 (all L digits)
+template <class C> BBK_DEV int bin_of_pos(int pos) {
+    constexpr int RL = C::radix(C::L - 1);
+    int q = pos % RL;
+    int u = pos / RL;
+    return bin_of_sub<C>(u) + (C::N / RL) * q;
+}
+// inverse: shared-memory position that holds output bin k after the last stage
+template <class C> BBK_DEV int pos_of_bin(int k) {
+    int pos = 0;
+    int rem = k;
+    static_for<0, C::L>([&](auto ss) {
+        constexpr int s = decltype(ss)::value;
+        pos = pos * C::radix(s) + rem % C::radix(s);
+        rem /= C::radix(s);
+    });
+    return pos;
+}
+
+template <class C> struct batch_index {
+    u64 m, k;
+    bool ok;
+};
+
+// One Stockham pass.  SRC/DST select where the elements come from / go to.
+enum : int { IO_GLOBAL = 0, IO_SMEM = 1 };
+
+template <class C, int S, int SRC, int DST>
+BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
+                       bool ok) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    constexpr int R = C::radix(S);
+    constexpr int NS = G::ns(S);
+    constexpr int NS1 = NS / R;
+    constexpr int NSUB = C::N / R;
+    constexpr int CNT = (NSUB + C::T - 1) / C::T;
+    constexpr bool LAST = (S == C::L - 1);
+    using WR = typename C::template WR<S>;
+    const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + C::tw_off(S);
+
+    cx<T> v[CNT][R];
+    // ---- gather
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int u = t + C::T * i;
+        if (NSUB % C::T == 0 || u < NSUB) {
+            const int n2 = u % NS1, q = u / NS1;
+            const int base = q * NS + n2;
+            static_for<0, R>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                const int pos = base + NS1 * j;
+                if constexpr (SRC == IO_GLOBAL) {
+                    if (ok) {
+                        v[i][j] = C::ld(a.in, m + u64(pos) * C::is1(a) + k * C::is2(a));
+                    } else {
+                        v[i][j] = cx<T>{T(0), T(0)};
+                    }
+                } else {
+                    v[i][j] = sm[G::soff(b, pos)];
+                }
+            });
+        }
+    });
+    // ---- butterflies + inter-stage twiddles
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int u = t + C::T * i;
+        if (NSUB % C::T == 0 || u < NSUB) {
+            reg_fft<T, WR, R, C::DIR>::run(v[i]);
+            if constexpr (!LAST) {
+                const int n2 = u % NS1;
+                static_for<1, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    cx<T> w = ldg_cx(tw + (q - 1) * NS1 + n2);
+                    v[i][q] = cmul(v[i][q], w);
+                });
+            }
+        }
+    });
+    // ---- scatter
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int u = t + C::T * i;
+        if (NSUB % C::T == 0 || u < NSUB) {
+            if constexpr (DST == IO_GLOBAL) {
+                static_assert(LAST, "only the last stage stores to global memory");
+                const int k0 = bin_of_sub<C>(u);
+                if (ok) {
+                    static_for<0, R>([&](auto qq) {
+                        constexpr int q = decltype(qq)::value;
+                        const int bin = k0 + (C::N / R) * q;
+                        C::st(a.out, m + u64(bin) * C::os1(a) + k * C::os2(a), v[i][q]);
+                    });
+                }
+            } else {
+                const int n2 = u % NS1, qi = u / NS1;
+                const int base = qi * NS + n2;
+                static_for<0, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    sm[G::soff(b, base + NS1 * q)] = v[i][q];
+                });
+            }
+        }
+    });
+}
+
+#ifdef BBFFT_EMU
+#define BBK_SYNC() ::bbfft_emu::syncthreads()
+#define BBK_TID() (::bbfft_emu::thread_idx())
+#define BBK_BID() (::bbfft_emu::block_idx())
+#define BBK_SMEM() (::bbfft_emu::shared_mem())
+#else
+#define BBK_SYNC() __syncthreads()
+#define BBK_TID() (int(threadIdx.x))
+#define BBK_BID() (u64(blockIdx.x))
+#define BBK_SMEM() (bbk_dyn_smem)
+extern __shared__ __align__(16) unsigned char bbk_dyn_smem[];
+#endif
+
+// stages S..L-1 with all intermediate exchanges in shared memory
+template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+    if constexpr (S < C::L) {
+        constexpr int SRC = (S == 0) ? SRC0 : IO_SMEM;
+        constexpr int DST = (S == C::L - 1) ? DSTL : IO_SMEM;
+        if constexpr (S > 0) {
+            BBK_SYNC();
+        }
+        run_stage<C, S, SRC, DST>(a, sm, t, b, m, k, ok);
+        run_stages<C, S + 1, SRC0, DSTL>(a, sm, t, b, m, k, ok);
+    }
+}
+
+// Cooperative, coalesced copy of the CTA's batch of rows between global and shared memory.
+// NROW = row length in elements of type E, rows are addressed (m, n, k) -> m + n*s1 + k*s2.
+template <class C, class E, int NROW, bool TO_SMEM, bool REVERSE, class LD, class ST>
+BBK_DEV void coop_copy(E *sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, int tid, LD ld, ST st) {
+    using G = geom<C>;
+    // iterate (ml, n, bh) with ml fastest so that consecutive threads touch consecutive addresses
+    constexpr int MLC = C::KLANES ? 1 : C::ML;          // m entries per CTA
+    constexpr int KB = C::KLANES ? C::ML * C::BH : C::BH; // k entries per CTA
+    constexpr int TOTAL = MLC * NROW * KB;
+    for (int idx = tid; idx < TOTAL; idx += G::THREADS) {
+        const int ml = idx % MLC;
+        const int n = (idx / MLC) % NROW;
+        const int kb = idx / (MLC * NROW);
+        const u64 m = m0 + ml, k = k0 + kb;
+        if (m < Mtot && k < K) {
+            const int b = C::KLANES ? kb : ml + C::ML * kb;
+            int pos = n;
+            if constexpr (REVERSE) {
+                pos = pos_of_bin<C>(n);
+            }
+            const u64 g = m + u64(n) * s1 + k * s2;
+            if constexpr (TO_SMEM) {
+                sm[G::soff(b, pos)] = ld(g);
+            } else {
+                st(g, sm[G::soff(b, pos)]);
+            }
+        }
+    }
+}
+
+template <class C> BBK_DEV void fft1d(args const &a) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const int l0 = tid % C::ML;
+    const int t = (tid / C::ML) % C::T;
+    const int bh = tid / (C::ML * C::T);
+    const int b = l0 + C::ML * bh;
+    const u64 bid = BBK_BID();
+    u64 m, k, m0, k0;
+    if constexpr (C::KLANES) {
+        m0 = 0;
+        k0 = bid * G::B;
+        m = 0;
+        k = k0 + b;
+    } else {
+        constexpr u64 MBLKS = (C::M + C::ML - 1) / C::ML;
+        m0 = (bid % MBLKS) * C::ML;
+        k0 = (bid / MBLKS) * C::BH;
+        m = m0 + l0;
+        k = k0 + bh;
+    }
+    const bool ok = (m < C::M) && (k < a.K);
+
+    if constexpr (C::MODE == C2C) {
+        constexpr int SRC0 = C::LOAD_STAGED ? IO_SMEM : IO_GLOBAL;
+        constexpr int DSTL = C::STORE_STAGED ? IO_SMEM : IO_GLOBAL;
+        if constexpr (C::LOAD_STAGED) {
+            coop_copy<C, cx<T>, C::N, true, false>(
+                sm, m0, k0, C::M, a.K, C::is1(a), C::is2(a), tid,
+                [&](u64 g) { return C::ld(a.in, g); }, [&](u64, cx<T>) {});
+            BBK_SYNC();
+        }
+        run_stages<C, 0, SRC0, DSTL>(a, sm, t, b, m, k, ok);
+        if constexpr (C::STORE_STAGED) {
+            BBK_SYNC();
+            coop_copy<C, cx<T>, C::N, false, true>(
+                sm, m0, k0, C::M, a.K, C::os1(a), C::os2(a), tid, [&](u64) { return cx<T>{}; },
+                [&](u64 g, cx<T> v) { C::st(a.out, g, v); });
+        }
+    }
+}
+
+} // namespace bbk
+
+#endif // BBFFT_KERNELS_CUH

@@ -1,0 +1,320 @@
+// plan.cpp -- plan objects of the CUDA backend: fft1d_plan (one kernel launch per execute),
+// nd_plan (2d/3d as chained double-batched 1d passes), make_plan, generate_fft_kernels.
+//
+// Replaces, for the CUDA backend, the reference's
+//   src/common/algorithm.hpp:20-30            select_fft_algorithm
+//   src/common/algorithm_1d.hpp:19-36         select_1d_fft_algorithm
+//   src/common/algorithm/small_batch_fft.hpp  + factor2_slm_fft.hpp   (1d plans)
+//   src/common/algorithm/nd_fft.hpp:27-152    (2d/3d)
+//   src/sycl/plan.cpp:16-24                   make_plan
+//   src/base/generator.cpp:16-25              generate_fft_kernels
+#include "plan.hpp"
+
+#include "bbfft/cuda/error.hpp"
+
+#include "bbfft/cuda/online_compiler.hpp"
+
+#include <dlfcn.h>
+
+#include <fstream>
+#include <iterator>
+#include <map>
+#include <mutex>
+#include <ostream>
+#include <sstream>
+
+namespace bbfft::cuda {
+
+// ------------------------------------------------------------------------------------------
+// configuration -> planner problem
+// ------------------------------------------------------------------------------------------
+static std::string translate_callbacks(user_module const &um, precision fp) {
+    std::string src(um.data, um.length);
+    if (um.language == kernel_language::cuda_c) return src;
+    // OpenCL-C callbacks (reference: test/callback.cpp:55-63,151-158): map the address space
+    // qualifiers away and give float2/double2 the OpenCL conversions the sources rely on
+    // (scalar -> vector broadcast, component-wise arithmetic).
+    (void)fp;
+    std::ostringstream os;
+    os << "namespace bbfft_ocl {\n"
+          "template <class T> struct vec2 {\n"
+          "    T x, y;\n"
+          "    __device__ vec2() {}\n"
+          "    __device__ vec2(T a, T b) : x(a), y(b) {}\n"
+          "    __device__ vec2(T a) : x(a), y(a) {}\n"
+          "    __device__ vec2(int a) : x(T(a)), y(T(a)) {}\n"
+          "};\n"
+          "template <class T> __device__ vec2<T> operator+(vec2<T> a, vec2<T> b) { return vec2<T>(a.x + b.x, a.y + b.y); }\n"
+          "template <class T> __device__ vec2<T> operator-(vec2<T> a, vec2<T> b) { return vec2<T>(a.x - b.x, a.y - b.y); }\n"
+          "template <class T> __device__ vec2<T> operator*(vec2<T> a, vec2<T> b) { return vec2<T>(a.x * b.x, a.y * b.y); }\n"
+          "template <class T> __device__ vec2<T> operator*(vec2<T> a, T s) { return vec2<T>(a.x * s, a.y * s); }\n"
+          "template <class T> __device__ vec2<T> operator*(T s, vec2<T> a) { return vec2<T>(a.x * s, a.y * s); }\n"
+          "template <class T> __device__ vec2<T> operator/(vec2<T> a, T s) { return vec2<T>(a.x / s, a.y / s); }\n"
+          "}\n"
+          "#define float2 bbfft_ocl::vec2<float>\n"
+          "#define double2 bbfft_ocl::vec2<double>\n"
+          "#define global\n#define local\n#define constant const\n#define private\n"
+          "#define __global\n#define __local\n#define __constant const\n#define __private\n"
+          "typedef unsigned int uint;\ntypedef unsigned long ulong;\ntypedef unsigned short ushort;\n"
+          "typedef unsigned char uchar;\n";
+    os << src << "\n";
+    os << "#undef global\n#undef local\n#undef constant\n#undef private\n";
+    return os.str();
+}
+
+problem_1d to_problem(configuration const &cfg) {
+    if (cfg.dim != 1) throw bad_configuration("internal: 1d problem expected");
+    if (cfg.istride[0] != 1 || cfg.ostride[0] != 1) {
+        throw bad_configuration("stride[0] must be 1 for input and output tensor");
+    }
+    if (cfg.fp != precision::f32 && cfg.fp != precision::f64) {
+        throw bad_configuration("unsupported precision");
+    }
+    if ((cfg.type == transform_type::r2c && cfg.dir != direction::forward) ||
+        (cfg.type == transform_type::c2r && cfg.dir != direction::backward)) {
+        throw bad_configuration("r2c direction must be forward and c2r direction must be backward");
+    }
+    if (cfg.shape[0] == 0 || cfg.shape[1] == 0) throw bad_configuration("empty FFT shape");
+    problem_1d p;
+    p.fp = static_cast<int>(cfg.fp);
+    p.dir = static_cast<int>(cfg.dir);
+    p.type = static_cast<int>(cfg.type);
+    p.M = cfg.shape[0];
+    p.N = cfg.shape[1];
+    p.K = cfg.shape[2];
+    p.is1 = std::int64_t(cfg.istride[1]);
+    p.is2 = std::int64_t(cfg.istride[2]);
+    p.os1 = std::int64_t(cfg.ostride[1]);
+    p.os2 = std::int64_t(cfg.ostride[2]);
+    if (cfg.callbacks) {
+        p.cb_source = translate_callbacks(cfg.callbacks, cfg.fp);
+        if (cfg.callbacks.load_function) p.cb_load = cfg.callbacks.load_function;
+        if (cfg.callbacks.store_function) p.cb_store = cfg.callbacks.store_function;
+    }
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// built-in ahead-of-time bundle: builtin_kernels.cubin next to this shared library, compiled by
+// nvcc at build time from generate_fft_kernels output (aot.py).  One module per device.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct builtin_bundle {
+    std::vector<char> image;
+    bool tried = false;
+    std::mutex mtx;
+    std::map<int, aot_module> per_device;
+};
+builtin_bundle &bundle() {
+    static builtin_bundle b;
+    return b;
+}
+} // namespace
+
+shared_handle<module_handle_t> builtin_module(std::string const &kernel_name, int device) {
+    auto &b = bundle();
+    std::lock_guard<std::mutex> lock(b.mtx);
+    if (!b.tried) {
+        b.tried = true;
+        char const *off = std::getenv("BBFFT_CUDA_NO_BUILTIN");
+        Dl_info info;
+        if (!(off && *off == '1') && dladdr(reinterpret_cast<void *>(&builtin_module), &info) && info.dli_fname) {
+            std::string path(info.dli_fname);
+            auto slash = path.find_last_of('/');
+            path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/builtin_kernels.cubin";
+            std::ifstream f(path, std::ios::binary);
+            if (f) b.image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+        }
+    }
+    if (b.image.empty()) return {};
+    auto it = b.per_device.find(device);
+    if (it == b.per_device.end()) {
+        try {
+            auto m = create_aot_module(reinterpret_cast<std::uint8_t const *>(b.image.data()), b.image.size(),
+                                       module_format::native, device);
+            it = b.per_device.emplace(device, std::move(m)).first;
+        } catch (std::exception const &) {
+            b.image.clear(); // unusable on this device (e.g. other architecture): fall back to JIT
+            return {};
+        }
+    }
+    if (it->second.kernel_names.count(kernel_name)) return it->second.mod;
+    return {};
+}
+
+static std::string env_tune() {
+    char const *t = std::getenv("BBFFT_CUDA_TUNE");
+    return t ? std::string(t) : std::string();
+}
+
+// ------------------------------------------------------------------------------------------
+// 1d
+// ------------------------------------------------------------------------------------------
+fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::string const &tune)
+    : api_(std::move(a)) {
+    auto prob = to_problem(cfg);
+    K_ = prob.K;
+    kp_ = plan_kernel_1d(prob, api_.props(), tune.empty() ? env_tune() : tune);
+    jit_cache_key key{kp_.identifier, api_.device_id()};
+    if (cache) module_ = cache->get(key);
+    if (!module_ && prob.cb_source.empty()) module_ = builtin_module(kp_.identifier, api_.device());
+    if (!module_) {
+        module_ = api_.build_module(kp_.source);
+        if (cache) cache->store(key, module_);
+    }
+    kernel_ = api_.create_kernel(module_.get(), kp_.identifier, kp_.p.smem_bytes);
+    twiddle_ = api_.create_twiddle_table(kp_.twiddle, kp_.p.fp);
+}
+
+fft1d_plan::~fft1d_plan() { api_.release_buffer(twiddle_); }
+
+void fft1d_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
+    if (in == out && kp_.inplace_unsupported) {
+        throw bad_configuration("The plan does not support in-place transform on the current device.");
+    }
+    kernel_args a;
+    a.in = in;
+    a.out = out;
+    a.tw = twiddle_;
+    a.K = K_;
+    a.M = kp_.p.M;
+    a.is1 = kp_.p.is1;
+    a.is2 = kp_.p.is2;
+    a.os1 = kp_.p.os1;
+    a.os2 = kp_.p.os2;
+    api_.launch_kernel(kernel_, kp_.p.grid(K_), kp_.p.threads, kp_.p.smem_bytes, a, stream);
+}
+
+auto plan_base::execute(void const *in, void *out, std::vector<event> const &dep_events) -> event {
+    cudaStream_t s = stream();
+    for (auto const &e : dep_events) {
+        if (e) BBFFT_CUDA_CHECK(cudaStreamWaitEvent(s, e.native(), 0));
+    }
+    enqueue(in, out, s);
+    return event(s);
+}
+
+// ------------------------------------------------------------------------------------------
+// nd: chained double-batched 1d passes (pass d: M_d = M * prod_{e<d} Nc_e, K_d = prod_{e>d} Nc_e * K)
+// ------------------------------------------------------------------------------------------
+void nd_passes(configuration const &cfg, std::function<void(configuration const &)> const &visit) {
+    const unsigned dim = cfg.dim;
+    if (cfg.callbacks) {
+        throw bad_configuration("User modules are unsuported for FFT dimension > 1.");
+    }
+    auto same = [&](tensor_extent const &x, tensor_extent const &y) {
+        for (unsigned d = 0; d < cfg.dim + 2; ++d) {
+            if (x[d] != y[d]) return false;
+        }
+        return true;
+    };
+    auto is_default = [&](bool inplace) {
+        return same(cfg.istride, default_istride(cfg.dim, cfg.shape, cfg.type, inplace)) &&
+               same(cfg.ostride, default_ostride(cfg.dim, cfg.shape, cfg.type, inplace));
+    };
+    bool inplace_layout = is_default(true);
+    if (!inplace_layout && !is_default(false)) {
+        throw bad_configuration("Only default tensor layouts are supported for the nd_fft.");
+    }
+    const bool real = cfg.type != transform_type::c2c;
+    auto n_spectrum = [&](unsigned d) { return (d == 0 && real) ? cfg.shape[1] / 2 + 1 : cfg.shape[d + 1]; };
+    auto n_signal = [&](unsigned d) {
+        return (d == 0 && real && inplace_layout) ? 2 * (cfg.shape[1] / 2 + 1) : cfg.shape[d + 1];
+    };
+    std::size_t right = cfg.shape[dim + 1];
+    for (unsigned d = 0; d < dim; ++d) right *= n_spectrum(d);
+    std::size_t left = cfg.shape[0];
+    std::vector<configuration> pass(dim);
+    for (unsigned d = 0; d < dim; ++d) {
+        right /= n_spectrum(d);
+        configuration c = {};
+        c.dim = 1;
+        c.shape = {left, cfg.shape[d + 1], right, 0, 0};
+        c.fp = cfg.fp;
+        c.dir = cfg.dir;
+        c.type = d == 0 ? cfg.type : transform_type::c2c;
+        c.istride = {1, left, left * n_signal(d), 0, 0};
+        c.ostride = {1, left, left * n_spectrum(d), 0, 0};
+        if (cfg.type == transform_type::c2r) std::swap(c.istride, c.ostride);
+        pass[d] = c;
+        left *= n_spectrum(d);
+    }
+    for (unsigned d = 0; d < dim; ++d) {
+        // c2r runs the modes in reverse so that the real mode comes last
+        visit(cfg.type == transform_type::c2r ? pass[dim - 1 - d] : pass[d]);
+    }
+}
+
+nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::move(a)), dim_(cfg.dim) {
+    nd_passes(cfg, [&](configuration const &c) {
+        plans_.push_back(std::make_shared<fft1d_plan>(c, api_, cache));
+    });
+    std::size_t real_bytes = static_cast<std::size_t>(cfg.fp);
+    std::size_t ibytes = (cfg.type == transform_type::r2c ? 1 : 2) * real_bytes;
+    std::size_t obytes = (cfg.type == transform_type::c2r ? 1 : 2) * real_bytes;
+    std::size_t isize = cfg.istride[dim_ + 1] * cfg.shape[dim_ + 1] * ibytes;
+    std::size_t osize = cfg.ostride[dim_ + 1] * cfg.shape[dim_ + 1] * obytes;
+    if (isize > osize) tmp_ = api_.create_device_buffer(isize);
+}
+
+nd_plan::~nd_plan() { api_.release_buffer(tmp_); }
+
+void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
+    void *tmp = tmp_ ? tmp_ : out;
+    plans_[0]->enqueue(in, tmp, stream);
+    for (unsigned d = 1; d + 1 < dim_; ++d) plans_[d]->enqueue(tmp, tmp, stream);
+    plans_[dim_ - 1]->enqueue(tmp, out, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// factory
+// ------------------------------------------------------------------------------------------
+std::shared_ptr<plan_base> select_fft_algorithm(configuration const &cfg, api a, jit_cache *cache) {
+    if (cfg.dim == 0 || cfg.dim > max_fft_dim) {
+        throw bad_configuration("Unsupported FFT dimension: " + std::to_string(cfg.dim));
+    }
+    if (cfg.dim == 1) return std::make_shared<fft1d_plan>(cfg, std::move(a), cache);
+    return std::make_shared<nd_plan>(cfg, std::move(a), cache);
+}
+
+} // namespace bbfft::cuda
+
+namespace bbfft {
+
+auto make_plan(configuration const &cfg, cudaStream_t stream, jit_cache *cache) -> cuda_plan {
+    return cuda_plan(cuda::select_fft_algorithm(cfg, cuda::api(stream), cache));
+}
+
+auto make_plan(configuration const &cfg, cudaStream_t stream, int device, jit_cache *cache) -> cuda_plan {
+    BBFFT_CUDA_CHECK(cudaSetDevice(device));
+    return cuda_plan(cuda::select_fft_algorithm(cfg, cuda::api(stream, device), cache));
+}
+
+// Offline generation needs no device: plan every configuration against `info` and print the
+// stubs (reference: src/base/generator.cpp:16-25 runs the plan selection against dummy_api).
+std::vector<std::string> generate_fft_kernels(std::ostream &os, std::vector<configuration> const &cfgs,
+                                              device_info const &info) {
+    cuda::device_props dev;
+    if (info.max_work_group_size) dev.max_threads_per_block = int(info.max_work_group_size);
+    if (info.local_memory_size) dev.max_smem_per_block = info.local_memory_size;
+    std::vector<std::string> names;
+    auto emit = [&](configuration const &c1) {
+        auto kp = cuda::plan_kernel_1d(cuda::to_problem(c1), dev, std::string());
+        for (auto const &n : names) {
+            if (n == kp.identifier) return;
+        }
+        names.push_back(kp.identifier);
+        os << kp.source << "\n";
+    };
+    for (auto const &cfg : cfgs) {
+        if (cfg.dim == 1) {
+            emit(cfg);
+        } else {
+            // same decomposition as nd_plan, without a device
+            cuda::nd_passes(cfg, emit);
+        }
+    }
+    return names;
+}
+
+} // namespace bbfft

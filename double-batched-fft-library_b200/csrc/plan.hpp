@@ -1,0 +1,79 @@
+// plan.hpp -- internal: plan implementation classes of the CUDA backend (see plan.cpp).
+#ifndef BBFFT_CUDA_PLAN_HPP
+#define BBFFT_CUDA_PLAN_HPP
+
+#include "bbfft/api.hpp"
+#include "bbfft/cuda/make_plan.hpp"
+#include "planner.hpp"
+#include "runtime.hpp"
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace bbfft::cuda {
+
+problem_1d to_problem(configuration const &cfg);
+
+// Decompose a 2d/3d configuration into its double-batched 1d passes, in execution order.
+void nd_passes(configuration const &cfg, std::function<void(configuration const &)> const &visit);
+
+class plan_base : public detail::plan_impl<event> {
+  public:
+    using detail::plan_impl<event>::execute;
+    // stream-ordered launch without event bookkeeping (used by the C ABI and by nd plans)
+    virtual void enqueue(void const *in, void *out, cudaStream_t stream) = 0;
+    virtual cudaStream_t stream() const = 0;
+    virtual unsigned launches_per_execute() const = 0;
+    auto execute(void const *in, void *out, std::vector<event> const &dep_events) -> event override;
+};
+
+class fft1d_plan : public plan_base {
+  public:
+    fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::string const &tune = std::string());
+    ~fft1d_plan() override;
+    fft1d_plan(fft1d_plan const &) = delete;
+    fft1d_plan &operator=(fft1d_plan const &) = delete;
+
+    void enqueue(void const *in, void *out, cudaStream_t stream) override;
+    cudaStream_t stream() const override { return api_.stream(); }
+    unsigned launches_per_execute() const override { return 1; }
+    kernel_plan const &kernel() const { return kp_; }
+
+  private:
+    api api_;
+    kernel_plan kp_;
+    std::uint64_t K_ = 0;
+    shared_handle<module_handle_t> module_;
+    cudaKernel_t kernel_ = nullptr;
+    void *twiddle_ = nullptr;
+};
+
+class nd_plan : public plan_base {
+  public:
+    nd_plan(configuration const &cfg, api a, jit_cache *cache);
+    ~nd_plan() override;
+    nd_plan(nd_plan const &) = delete;
+    nd_plan &operator=(nd_plan const &) = delete;
+
+    void enqueue(void const *in, void *out, cudaStream_t stream) override;
+    cudaStream_t stream() const override { return api_.stream(); }
+    unsigned launches_per_execute() const override { return dim_; }
+    std::vector<std::shared_ptr<fft1d_plan>> const &passes() const { return plans_; }
+
+  private:
+    api api_;
+    unsigned dim_;
+    std::vector<std::shared_ptr<fft1d_plan>> plans_;
+    void *tmp_ = nullptr;
+};
+
+// kernel from the built-in ahead-of-time bundle, or an empty handle
+shared_handle<module_handle_t> builtin_module(std::string const &kernel_name, int device);
+
+std::shared_ptr<plan_base> select_fft_algorithm(configuration const &cfg, api a, jit_cache *cache);
+
+} // namespace bbfft::cuda
+
+#endif

@@ -1,0 +1,744 @@
+// planner.cpp -- see planner.hpp.
+#include "planner.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <map>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+
+namespace bbfft::cuda {
+
+// ------------------------------------------------------------------------------------------
+// integer helpers
+// ------------------------------------------------------------------------------------------
+std::vector<int> prime_factors(int n) {
+    // ascending trial division (reference: src/base/prime_factorization.cpp:13-25)
+    std::vector<int> f;
+    for (int p = 2; p * p <= n; ++p) {
+        while (n % p == 0) {
+            f.push_back(p);
+            n /= p;
+        }
+    }
+    if (n > 1) {
+        f.push_back(n);
+    }
+    return f;
+}
+
+static int max_prime(int n) {
+    auto f = prime_factors(n);
+    return f.empty() ? 1 : f.back();
+}
+
+// A radix is computable by bbk::reg_fft when its prime factors have hand-written or generic
+// butterflies; generic odd primes are O(p^2) so keep them small inside composites.
+bool radix_supported(int r) {
+    if (r < 2) return false;
+    return true;
+}
+
+static int pow2_ceil(std::uint64_t x) {
+    int p = 1;
+    while (std::uint64_t(p) < x && p < (1 << 30)) p <<= 1;
+    return p;
+}
+
+std::uint64_t kernel_params::k_per_cta() const {
+    std::uint64_t per = klanes ? std::uint64_t(ML) * BH : std::uint64_t(BH);
+    if (mode == k_r2c_double || mode == k_c2r_double) per *= 2;
+    return per;
+}
+
+std::uint64_t kernel_params::grid(std::uint64_t K) const {
+    std::uint64_t per = k_per_cta();
+    std::uint64_t kblocks = (K + per - 1) / per;
+    std::uint64_t mblocks = klanes ? 1 : (M + ML - 1) / ML;
+    return kblocks * mblocks;
+}
+
+// ------------------------------------------------------------------------------------------
+// tuning string
+// ------------------------------------------------------------------------------------------
+static std::map<std::string, std::string> parse_tune(std::string const &tune) {
+    std::map<std::string, std::string> kv;
+    std::stringstream ss(tune);
+    std::string item;
+    while (std::getline(ss, item, ',')) {
+        auto eq = item.find('=');
+        if (eq == std::string::npos) continue;
+        kv[item.substr(0, eq)] = item.substr(eq + 1);
+    }
+    return kv;
+}
+
+static std::vector<int> parse_radices(std::string const &s) {
+    std::vector<int> r;
+    std::stringstream ss(s);
+    std::string item;
+    while (std::getline(ss, item, 'x')) {
+        r.push_back(std::atoi(item.c_str()));
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// factorization search
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct stage_choice {
+    std::vector<int> radix;
+    int T = 1;
+    int regs = 0;    // complex elements held per thread (max over stages)
+    double cost = 0; // lower is better
+};
+
+// relative arithmetic cost of a length-r in-register FFT (per element), rough
+double radix_cost(int r) {
+    double c = 0;
+    for (int p : prime_factors(r)) {
+        c += (p == 2) ? 1.0 : (p == 3 ? 1.8 : (p == 5 ? 2.6 : (p == 7 ? 3.4 : 0.5 * p)));
+    }
+    return c;
+}
+
+void enum_factorizations(int n, int max_r, int max_l, std::vector<int> &cur,
+                         std::vector<std::vector<int>> &out) {
+    if (n == 1) {
+        if (!cur.empty()) out.push_back(cur);
+        return;
+    }
+    if (int(cur.size()) >= max_l) return;
+    int lo = cur.empty() ? 2 : cur.back(); // ascending
+    for (int r = lo; r <= n && r <= max_r; ++r) {
+        if (n % r) continue;
+        cur.push_back(r);
+        enum_factorizations(n / r, max_r, max_l, cur, out);
+        cur.pop_back();
+    }
+}
+
+stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
+    const int single_max = (fp == 4) ? 32 : 16; // one thread holds the whole transform
+    stage_choice best;
+    best.cost = 1e30;
+    if (N <= single_max) {
+        best.radix = {N};
+        best.T = 1;
+        best.regs = N;
+        best.cost = 0;
+        return best;
+    }
+    double ideal = 0;
+    for (int p : prime_factors(N)) ideal += radix_cost(p);
+    // relax the register budget / thread limit until something fits
+    for (int relax = 0; relax < 4 && best.radix.empty(); ++relax) {
+        const int emax = std::max(16 << relax, max_prime(N)); // complex elements per thread
+        const int tmax = max_threads_per_transform << relax;
+        std::vector<std::vector<int>> facs;
+        std::vector<int> cur;
+        enum_factorizations(N, emax, 4, cur, facs);
+        for (auto const &f : facs) {
+            int L = int(f.size());
+            if (L < 2 && N > 64) continue;
+            std::set<int> tcand;
+            for (int r : f) {
+                for (int c = 1; c <= 8; ++c) {
+                    int nsub = N / r;
+                    tcand.insert((nsub + c - 1) / c);
+                }
+            }
+            if (L == 1) tcand = {1};
+            for (int T : tcand) {
+                if (T < 1 || T > tmax) continue;
+                int regs = 0, rsum = 0;
+                double work = 0;
+                for (int r : f) {
+                    int nsub = N / r;
+                    int cnt = (nsub + T - 1) / T;
+                    regs = std::max(regs, cnt * r);
+                    rsum += r;
+                    work += double(cnt) * T * r / N * radix_cost(r);
+                }
+                if (regs > emax) continue;
+                // cost: arithmetic (counting idle lanes) + exchange passes + mild preferences
+                // for ~8 elements per thread and for balanced radices
+                double cost = work / ideal + 0.35 * (L - 1);
+                cost += 0.02 * std::abs(std::log2(double(regs) / 8.0));
+                cost += 0.001 * rsum;
+                if (cost < best.cost - 1e-9) {
+                    best.cost = cost;
+                    best.radix = f;
+                    best.T = T;
+                    best.regs = regs;
+                }
+            }
+        }
+    }
+    if (best.radix.empty()) {
+        throw std::runtime_error("bbfft-cuda planner: no factorization found for N=" +
+                                 std::to_string(N));
+    }
+    return best;
+}
+
+// ---- shared memory bank-conflict model -----------------------------------------------------
+struct layout_eval {
+    kernel_params const &p;
+    int elem_bytes;
+    int pad(int pos, int padk) const { return padk > 0 ? pos + pos / padk : pos; }
+    int soff(int b, int pos, int padk, int row) const {
+        if (p.LL > 1) return (b % p.LL) + p.LL * pad(pos, padk) + row * (b / p.LL);
+        return pad(pos, padk) + row * b;
+    }
+    // wavefronts needed by one warp-wide access (addresses in elements; -1 = inactive lane)
+    int wavefronts(std::vector<int> const &off) const {
+        int lanes_per_group = std::max(1, 32 * 4 / elem_bytes); // 16 for 8 B, 8 for 16 B
+        int total = 0;
+        for (int g = 0; g < 32; g += lanes_per_group) {
+            std::map<int, std::set<int>> bank_words;
+            bool any = false;
+            for (int l = g; l < g + lanes_per_group && l < 32; ++l) {
+                if (off[l] < 0) continue;
+                any = true;
+                long byte = long(off[l]) * elem_bytes;
+                for (int w = 0; w < elem_bytes / 4; ++w) {
+                    int word = int(byte / 4) + w;
+                    bank_words[word % 32].insert(word);
+                }
+            }
+            if (!any) continue;
+            std::size_t mx = 1;
+            for (auto &kv : bank_words) mx = std::max(mx, kv.second.size());
+            total += int(mx);
+        }
+        return total;
+    }
+    int ideal(std::vector<int> const &off) const {
+        int lanes_per_group = std::max(1, 32 * 4 / elem_bytes);
+        int total = 0;
+        for (int g = 0; g < 32; g += lanes_per_group) {
+            for (int l = g; l < g + lanes_per_group && l < 32; ++l) {
+                if (off[l] >= 0) {
+                    ++total;
+                    break;
+                }
+            }
+        }
+        return total;
+    }
+    static int pos_of_bin(kernel_params const &p, int k) {
+        int pos = 0, rem = k;
+        for (int s = 0; s < p.L; ++s) {
+            pos = pos * p.radix[s] + rem % p.radix[s];
+            rem /= p.radix[s];
+        }
+        return pos;
+    }
+    // excess wavefronts over all shared-memory phases of the kernel for warps 0 and 1
+    long score(int padk, int row) const {
+        long excess = 0;
+        int threads = p.threads;
+        for (int warp = 0; warp < std::min(2, (threads + 31) / 32); ++warp) {
+            // stage accesses
+            for (int s = 0; s < p.L; ++s) {
+                bool reads = (s > 0) || p.load_staged;
+                bool writes = (s < p.L - 1) || p.store_staged;
+                if (!reads && !writes) continue;
+                int R = p.radix[s];
+                int NS = p.N;
+                for (int i = 0; i < s; ++i) NS /= p.radix[i];
+                int NS1 = NS / R, NSUB = p.N / R;
+                int CNT = (NSUB + p.T - 1) / p.T;
+                for (int i = 0; i < CNT; ++i) {
+                    for (int j = 0; j < R; ++j) {
+                        std::vector<int> off(32, -1);
+                        for (int l = 0; l < 32; ++l) {
+                            int tid = warp * 32 + l;
+                            if (tid >= threads) continue;
+                            int l0 = tid % p.ML, t = (tid / p.ML) % p.T, bh = tid / (p.ML * p.T);
+                            int b = l0 + p.ML * bh;
+                            int u = t + p.T * i;
+                            if (u >= NSUB) continue;
+                            int n2 = u % NS1, q = u / NS1;
+                            off[l] = soff(b, q * NS + n2 + NS1 * j, padk, row);
+                        }
+                        int e = wavefronts(off) - ideal(off);
+                        excess += e * ((reads ? 1 : 0) + (writes ? 1 : 0));
+                    }
+                }
+            }
+            // cooperative copies
+            int mlc = p.klanes ? 1 : p.ML;
+            int kb = p.klanes ? p.ML * p.BH : p.BH;
+            int total = mlc * p.N * kb;
+            for (int pass = 0; pass < 2; ++pass) {
+                bool active = pass == 0 ? p.load_staged : p.store_staged;
+                if (!active || p.mode != k_c2c) continue;
+                for (int it = 0; it < 4; ++it) {
+                    std::vector<int> off(32, -1);
+                    for (int l = 0; l < 32; ++l) {
+                        int idx = it * threads + warp * 32 + l;
+                        if (idx >= total) continue;
+                        int ml = idx % mlc, n = (idx / mlc) % p.N, kk = idx / (mlc * p.N);
+                        int b = p.klanes ? kk : ml + p.ML * kk;
+                        int pos = pass == 0 ? n : pos_of_bin(p, n);
+                        off[l] = soff(b, pos, padk, row);
+                    }
+                    excess += wavefronts(off) - ideal(off);
+                }
+            }
+        }
+        return excess;
+    }
+};
+
+void choose_smem_layout(kernel_params &p) {
+    const int elem_bytes = 2 * p.fp;
+    bool uses_smem = p.L > 1 || p.load_staged || p.store_staged || p.mode != k_c2c;
+    p.LL = (p.klanes || p.ML == 1) ? 1 : p.ML;
+    int rowlen = p.N + ((p.mode == k_r2c_half || p.mode == k_c2r_half) ? 1 : 0);
+    if (!uses_smem) {
+        p.PADK = 0;
+        p.ROW = p.LL * rowlen;
+        p.smem_bytes = 0;
+        return;
+    }
+    layout_eval ev{p, elem_bytes};
+    long best_score = -1;
+    int best_padk = 0, best_row = p.LL * rowlen;
+    std::vector<int> padks = {0};
+    if (p.LL * elem_bytes < 128) {
+        for (int k : {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 20, 24, 25, 27, 28, 32, 64}) {
+            if (k < rowlen) padks.push_back(k);
+        }
+    }
+    for (int padk : padks) {
+        int padded = ev.pad(rowlen - 1, padk) + 1;
+        int max_extra = (p.LL * elem_bytes >= 128) ? 0 : 17;
+        for (int extra = 0; extra <= max_extra; ++extra) {
+            int row = p.LL * padded + extra;
+            long sc = ev.score(padk, row);
+            // prefer less memory on ties
+            long key = sc * 4096 + (row - p.LL * rowlen);
+            if (best_score < 0 || key < best_score) {
+                best_score = key;
+                best_padk = padk;
+                best_row = row;
+            }
+        }
+    }
+    p.PADK = best_padk;
+    p.ROW = best_row;
+    int groups = (p.batch_per_cta() + p.LL - 1) / p.LL;
+    p.smem_bytes = std::size_t(groups) * p.ROW * elem_bytes;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
+                           std::string const &tune_str) {
+    if (prob.N < 1 || prob.M < 1) {
+        throw std::runtime_error("bbfft-cuda planner: empty shape");
+    }
+    if (prob.N > 8192) {
+        throw std::runtime_error("bbfft-cuda planner: N too large for the single-kernel path");
+    }
+    auto tune = parse_tune(tune_str);
+    kernel_plan plan;
+    kernel_params &p = plan.p;
+    p.fp = prob.fp;
+    p.dir = prob.dir;
+    p.M = prob.M;
+    p.is1 = prob.is1;
+    p.is2 = prob.is2;
+    p.os1 = prob.os1;
+    p.os2 = prob.os2;
+    p.nreal = int(prob.N);
+    p.cb_load = prob.cb_load;
+    p.cb_store = prob.cb_store;
+    const bool real = prob.type != 0;
+    if (!real) {
+        p.mode = k_c2c;
+        p.N = int(prob.N);
+    } else if (prob.N % 2 == 0) {
+        p.mode = prob.type == 1 ? k_r2c_half : k_c2r_half;
+        p.N = int(prob.N / 2);
+    } else {
+        p.mode = prob.type == 1 ? k_r2c_double : k_c2r_double;
+        p.N = int(prob.N);
+    }
+    const int elem_bytes = 2 * p.fp;
+
+    // ---- batch lanes
+    const int full_lanes = 128 / elem_bytes; // lanes that make one 128-byte row
+    if (prob.M == 1) {
+        p.ML = 1;
+    } else {
+        int ml = pow2_ceil(prob.M);
+        p.ML = std::min(ml, full_lanes);
+        if (prob.M > std::uint64_t(full_lanes) && prob.M % full_lanes != 0) {
+            // pick the lane count that wastes the fewest lanes in the last m block
+            int best = full_lanes;
+            std::uint64_t best_waste = ~0ull;
+            for (int c : {full_lanes, full_lanes / 2, 2 * full_lanes}) {
+                if (c < 2 || c > 32) continue;
+                std::uint64_t waste = (prob.M + c - 1) / c * c - prob.M;
+                if (waste < best_waste || (waste == best_waste && c > best)) {
+                    best_waste = waste;
+                    best = c;
+                }
+            }
+            p.ML = best;
+        }
+    }
+    if (tune.count("ML")) p.ML = std::atoi(tune["ML"].c_str());
+
+    // ---- stages
+    int max_tpt = std::max(1, 512 / p.ML);
+    stage_choice sc;
+    if (tune.count("R")) {
+        sc.radix = parse_radices(tune["R"]);
+        int prod = 1, maxr = 1;
+        for (int r : sc.radix) {
+            prod *= r;
+            maxr = std::max(maxr, r);
+        }
+        if (prod != p.N) throw std::runtime_error("bbfft-cuda planner: tune R does not multiply to N");
+        sc.T = sc.radix.size() == 1 ? 1 : p.N / maxr;
+    } else {
+        sc = choose_stages(p.N, p.fp, max_tpt);
+    }
+    if (tune.count("T")) sc.T = std::atoi(tune["T"].c_str());
+    p.L = int(sc.radix.size());
+    if (p.L > 4) throw std::runtime_error("bbfft-cuda planner: more than 4 stages");
+    for (int s = 0; s < 4; ++s) p.radix[s] = s < p.L ? sc.radix[s] : 1;
+    p.T = sc.T;
+    if (p.L == 1) p.T = 1;
+
+    // ---- M == 1, single thread per transform: let the lanes walk k
+    p.klanes = false;
+    if (prob.M == 1 && p.T == 1) {
+        p.klanes = true;
+        p.ML = 32;
+    }
+    if (tune.count("KL")) {
+        p.klanes = std::atoi(tune["KL"].c_str()) != 0;
+        if (p.klanes && prob.M != 1) throw std::runtime_error("bbfft-cuda planner: KL needs M == 1");
+    }
+
+    // ---- CTA size
+    int target_threads = 256;
+    int bh = std::max(1, target_threads / (p.ML * p.T));
+    // keep shared memory per CTA modest so that several CTAs share an SM
+    while (bh > 1 && std::size_t(p.ML) * bh * (p.N + 2) * elem_bytes > 48 * 1024) bh /= 2;
+    // do not make CTAs bigger than the batch
+    std::uint64_t kunits = (p.mode == k_r2c_double || p.mode == k_c2r_double) ? (prob.K + 1) / 2 : prob.K;
+    if (p.klanes) {
+        while (bh > 1 && std::uint64_t(p.ML) * (bh / 2) >= kunits) bh /= 2;
+    } else {
+        while (bh > 1 && std::uint64_t(bh / 2) >= kunits) bh /= 2;
+    }
+    p.BH = bh;
+    if (tune.count("BH")) p.BH = std::atoi(tune["BH"].c_str());
+    p.threads = p.ML * p.T * p.BH;
+    if (p.threads > dev.max_threads_per_block) {
+        throw std::runtime_error("bbfft-cuda planner: CTA too large");
+    }
+
+    // ---- staging: go through shared memory whenever the direct access would be poorly coalesced
+    const int seg_bytes = 32;
+    if (p.klanes) {
+        p.load_staged = true;
+        p.store_staged = true;
+    } else if (p.ML == 1) {
+        // lanes walk t: loads touch T consecutive elements, stores are digit-reversed
+        p.load_staged = p.T * elem_bytes < seg_bytes;
+        p.store_staged = true;
+    } else {
+        bool rows_ok = std::uint64_t(p.ML) * elem_bytes >= std::uint64_t(seg_bytes) && prob.M % p.ML == 0;
+        p.load_staged = !rows_ok && prob.M * elem_bytes < 64;
+        p.store_staged = !rows_ok && prob.M * elem_bytes < 64;
+    }
+    if (p.mode != k_c2c) {
+        // real transforms do their own pre/post passes (kernel decides), staging flags select
+        // the cooperative row copies
+        if (!(prob.M == 1)) {
+            p.load_staged = false;
+            p.store_staged = false;
+        }
+    }
+    // user callbacks see every element exactly once in either path, so staging stays legal.
+    if (tune.count("LD")) p.load_staged = std::atoi(tune["LD"].c_str()) != 0;
+    if (tune.count("ST")) p.store_staged = std::atoi(tune["ST"].c_str()) != 0;
+
+    choose_smem_layout(p);
+    if (tune.count("PADK") || tune.count("ROW")) {
+        if (tune.count("PADK")) p.PADK = std::atoi(tune["PADK"].c_str());
+        int rowlen = p.N + ((p.mode == k_r2c_half || p.mode == k_c2r_half) ? 1 : 0);
+        int padded = (p.PADK > 0 ? (rowlen - 1) + (rowlen - 1) / p.PADK : rowlen - 1) + 1;
+        p.ROW = std::max(p.LL * padded, tune.count("ROW") ? std::atoi(tune["ROW"].c_str()) : 0);
+        int groups = (p.batch_per_cta() + p.LL - 1) / p.LL;
+        p.smem_bytes = std::size_t(groups) * p.ROW * elem_bytes;
+    }
+    if (p.smem_bytes > dev.max_smem_per_block) {
+        throw std::runtime_error("bbfft-cuda planner: shared memory demand too large");
+    }
+    p.min_blocks = 1;
+
+    // real in-place transforms need one CTA to own every m of a k slice, like the reference
+    // (src/base/generator/small_batch_fft.cpp:38, factor2_slm_fft.cpp:63)
+    plan.inplace_unsupported = real && !p.klanes && std::uint64_t(p.ML) < prob.M;
+
+    plan.identifier = make_identifier(p);
+    plan.source = emit_stub(p, plan.identifier, prob.cb_source);
+    plan.twiddle = make_twiddles(p);
+    return plan;
+}
+
+// ------------------------------------------------------------------------------------------
+// identifier
+// ------------------------------------------------------------------------------------------
+std::string make_identifier(kernel_params const &p) {
+    // K is deliberately not part of the key (reference: jit_cache key = identifier + device,
+    // include/bbfft/jit_cache.hpp:23-41; K is a run-time argument)
+    static char const *mode_names[] = {"c2c", "r2ch", "c2rh", "r2cd", "c2rd"};
+    std::ostringstream os;
+    os << "bbfft_" << mode_names[p.mode] << (p.dir < 0 ? "_m1" : "_p1") << "_f" << (p.fp * 8)
+       << "_M" << p.M << "_N" << p.nreal << "_r";
+    for (int s = 0; s < p.L; ++s) os << (s ? "x" : "") << p.radix[s];
+    os << "_T" << p.T << "_ML" << p.ML << "_BH" << p.BH << "_kl" << int(p.klanes) << "_ld"
+       << int(p.load_staged) << "_st" << int(p.store_staged) << "_pk" << p.PADK << "_row" << p.ROW
+       << "_is" << p.is1 << "_" << p.is2 << "_os" << p.os1 << "_" << p.os2;
+    if (!p.cb_load.empty()) os << "_" << p.cb_load;
+    if (!p.cb_store.empty()) os << "_" << p.cb_store;
+    std::string s = os.str();
+    for (auto &c : s) {
+        if (c == '-') c = 'n';
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// twiddles
+// ------------------------------------------------------------------------------------------
+static void unit_root(long num, long den, int dir, double &re, double &im) {
+    // exp(dir * 2 pi i num/den), evaluated in long double with octant reduction
+    num %= den;
+    if (num < 0) num += den;
+    const long double tau = 6.283185307179586476925286766559005768L;
+    // reduce to first octant for symmetric, accurate values
+    long n8 = num * 8;
+    int oct = int(n8 / den);
+    long double c, s;
+    long double ang;
+    switch (oct) {
+    case 0:
+        ang = tau * num / den;
+        c = cosl(ang);
+        s = sinl(ang);
+        break;
+    case 1:
+        ang = tau * (den - 4 * num) / (4.0L * den); // pi/2 - x
+        c = sinl(ang);
+        s = cosl(ang);
+        break;
+    case 2:
+        ang = tau * (4 * num - den) / (4.0L * den); // x - pi/2
+        c = -sinl(ang);
+        s = cosl(ang);
+        break;
+    case 3:
+        ang = tau * (den - 2 * num) / (2.0L * den); // pi - x
+        c = -cosl(ang);
+        s = sinl(ang);
+        break;
+    case 4:
+        ang = tau * (2 * num - den) / (2.0L * den); // x - pi
+        c = -cosl(ang);
+        s = -sinl(ang);
+        break;
+    case 5:
+        ang = tau * (3 * den - 4 * num) / (4.0L * den); // 3pi/2 - x
+        c = -sinl(ang);
+        s = -cosl(ang);
+        break;
+    case 6:
+        ang = tau * (4 * num - 3 * den) / (4.0L * den); // x - 3pi/2
+        c = sinl(ang);
+        s = -cosl(ang);
+        break;
+    default:
+        ang = tau * (den - num) / (long double)den; // 2pi - x
+        c = cosl(ang);
+        s = -sinl(ang);
+        break;
+    }
+    re = double(c);
+    im = double(dir < 0 ? -s : s);
+}
+
+static std::vector<int> tw_offsets(kernel_params const &p, int *total) {
+    std::vector<int> off(4, 0);
+    int acc = 0;
+    int NS = p.N;
+    for (int s = 0; s < p.L; ++s) {
+        off[s] = acc;
+        int R = p.radix[s];
+        int NS1 = NS / R;
+        if (s < p.L - 1) acc += (R - 1) * NS1;
+        NS = NS1;
+    }
+    if (total) *total = acc;
+    return off;
+}
+
+std::vector<double> make_twiddles(kernel_params const &p) {
+    std::vector<double> tw;
+    int NS = p.N;
+    for (int s = 0; s + 1 < p.L; ++s) {
+        int R = p.radix[s];
+        int NS1 = NS / R;
+        for (int q = 1; q < R; ++q) {
+            for (int n2 = 0; n2 < NS1; ++n2) {
+                double re, im;
+                unit_root(long(n2) * q, NS, p.dir, re, im);
+                tw.push_back(re);
+                tw.push_back(im);
+            }
+        }
+        NS = NS1;
+    }
+    if (p.mode == k_r2c_half || p.mode == k_c2r_half) {
+        // post/pre twiddles for the half-length trick: w_{2N}^{dir*i}, i = 0..N/2
+        // (reference host table: src/common/algorithm/factor2_slm_fft.hpp:81-88)
+        for (int i = 0; i <= p.N / 2; ++i) {
+            double re, im;
+            unit_root(i, 2L * p.N, p.dir, re, im);
+            tw.push_back(re);
+            tw.push_back(im);
+        }
+    }
+    if (tw.empty()) {
+        tw.push_back(1.0);
+        tw.push_back(0.0);
+    }
+    return tw;
+}
+
+// ------------------------------------------------------------------------------------------
+// stub
+// ------------------------------------------------------------------------------------------
+static void emit_w_table(std::ostringstream &os, int R) {
+    os << "struct W" << R << " {\n    static constexpr int n = " << R << ";\n";
+    for (int part = 0; part < 2; ++part) {
+        os << "    static BBK_CE double " << (part ? "s" : "c") << "(int k) {\n        constexpr double t["
+           << R << "] = {";
+        for (int k = 0; k < R; ++k) {
+            double re, im;
+            unit_root(k, R, +1, re, im);
+            char buf[64];
+            std::snprintf(buf, sizeof(buf), "%.17g", part ? im : re);
+            os << (k ? ", " : "") << buf;
+        }
+        os << "};\n        return t[k];\n    }\n";
+    }
+    os << "};\n";
+}
+
+std::string emit_stub(kernel_params const &p, std::string const &identifier,
+                      std::string const &cb_source) {
+    std::ostringstream os;
+    const char *real = p.fp == 4 ? "float" : "double";
+    const char *vec = p.fp == 4 ? "float2" : "double2";
+    os << "// generated by bbfft-cuda planner -- do not edit\n";
+    os << "#include \"bbfft_kernels.cuh\"\n";
+    // every stub lives in its own namespace so that several can share a translation unit
+    os << "namespace stub_" << identifier << " {\n";
+    if (!cb_source.empty()) {
+        os << "// ---- user callbacks (reference: include/bbfft/user_module.hpp:24-37)\n";
+        os << cb_source << "\n";
+    }
+    std::set<int> rs;
+    for (int s = 0; s < p.L; ++s) rs.insert(p.radix[s]);
+    for (int r : rs) emit_w_table(os, r);
+    int tw_total = 0;
+    auto off = tw_offsets(p, &tw_total);
+    os << "struct C {\n";
+    os << "    using real_t = " << real << ";\n";
+    os << "    static constexpr int N = " << p.N << ", NREAL = " << p.nreal << ", DIR = " << p.dir
+       << ", MODE = " << p.mode << ", L = " << p.L << ", T = " << p.T << ", ML = " << p.ML
+       << ", BH = " << p.BH << ";\n";
+    os << "    static constexpr bool KLANES = " << (p.klanes ? "true" : "false")
+       << ", LOAD_STAGED = " << (p.load_staged ? "true" : "false")
+       << ", STORE_STAGED = " << (p.store_staged ? "true" : "false") << ";\n";
+    os << "    static constexpr bbk::u64 M = " << p.M << "ull;\n";
+    os << "    static constexpr int LL = " << p.LL << ", PADK = " << p.PADK << ", ROW = " << p.ROW
+       << ", TW_REAL = " << tw_total << ";\n";
+    os << "    static BBK_CE int radix(int s) {\n        constexpr int r[4] = {" << p.radix[0] << ", "
+       << p.radix[1] << ", " << p.radix[2] << ", " << p.radix[3] << "};\n        return r[s];\n    }\n";
+    os << "    static BBK_CE int tw_off(int s) {\n        constexpr int r[4] = {" << off[0] << ", "
+       << off[1] << ", " << off[2] << ", " << off[3] << "};\n        return r[s];\n    }\n";
+    // per-stage table type
+    os << "    template <int S, int Dummy = 0> struct WRsel;\n";
+    for (int s = 0; s < p.L; ++s) {
+        os << "    template <int Dummy> struct WRsel<" << s << ", Dummy> { using type = W" << p.radix[s]
+           << "; };\n";
+    }
+    os << "    template <int S> using WR = typename WRsel<S>::type;\n";
+    os << "    static BBK_DEV bbk::i64 is1(bbk::args const &) { return " << p.is1 << "ll; }\n";
+    os << "    static BBK_DEV bbk::i64 is2(bbk::args const &) { return " << p.is2 << "ll; }\n";
+    os << "    static BBK_DEV bbk::i64 os1(bbk::args const &) { return " << p.os1 << "ll; }\n";
+    os << "    static BBK_DEV bbk::i64 os2(bbk::args const &) { return " << p.os2 << "ll; }\n";
+    // element accessors; user callbacks are spliced in here
+    // (reference: callback_accessor, src/base/generator/tensor_accessor.cpp:34-55)
+    const bool in_real = p.mode == k_r2c_half || p.mode == k_r2c_double;
+    const bool out_real = p.mode == k_c2r_half || p.mode == k_c2r_double;
+    if (p.cb_load.empty()) {
+        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
+              "        return reinterpret_cast<const bbk::cx<real_t> *>(in)[off];\n    }\n";
+        os << "    static BBK_DEV real_t ldr(const void *in, bbk::u64 off) {\n"
+              "        return reinterpret_cast<const real_t *>(in)[off];\n    }\n";
+    } else if (in_real) {
+        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *, bbk::u64) { return bbk::cx<real_t>{}; }\n";
+        os << "    static BBK_DEV real_t ldr(const void *in, bbk::u64 off) {\n        return " << p.cb_load
+           << "(reinterpret_cast<" << real << " *>(const_cast<void *>(in)), off);\n    }\n";
+    } else {
+        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n        " << vec
+           << " r = " << p.cb_load << "(reinterpret_cast<" << vec
+           << " *>(const_cast<void *>(in)), off);\n        return bbk::cx<real_t>{r.x, r.y};\n    }\n";
+        os << "    static BBK_DEV real_t ldr(const void *, bbk::u64) { return real_t(0); }\n";
+    }
+    if (p.cb_store.empty()) {
+        os << "    static BBK_DEV void st(void *out, bbk::u64 off, bbk::cx<real_t> v) {\n"
+              "        reinterpret_cast<bbk::cx<real_t> *>(out)[off] = v;\n    }\n";
+        os << "    static BBK_DEV void str(void *out, bbk::u64 off, real_t v) {\n"
+              "        reinterpret_cast<real_t *>(out)[off] = v;\n    }\n";
+    } else if (out_real) {
+        os << "    static BBK_DEV void st(void *, bbk::u64, bbk::cx<real_t>) {}\n";
+        os << "    static BBK_DEV void str(void *out, bbk::u64 off, real_t v) {\n        " << p.cb_store
+           << "(reinterpret_cast<" << real << " *>(out), off, v);\n    }\n";
+    } else {
+        os << "    static BBK_DEV void st(void *out, bbk::u64 off, bbk::cx<real_t> v) {\n        " << vec
+           << " r;\n        r.x = v.x;\n        r.y = v.y;\n        " << p.cb_store << "(reinterpret_cast<"
+           << vec << " *>(out), off, r);\n    }\n";
+        os << "    static BBK_DEV void str(void *, bbk::u64, real_t) {}\n";
+    }
+    os << "    static constexpr bool HAS_CALLBACKS = "
+       << ((p.cb_load.empty() && p.cb_store.empty()) ? "false" : "true") << ";\n";
+    os << "};\n} // namespace stub_" << identifier << "\n";
+    os << "extern \"C\" BBK_GLOBAL void BBK_LAUNCH_BOUNDS(" << p.threads << ", " << p.min_blocks << ") "
+       << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
+    return os.str();
+}
+
+} // namespace bbfft::cuda

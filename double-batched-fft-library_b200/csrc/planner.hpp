@@ -1,0 +1,86 @@
+// planner.hpp -- device-independent planning for the sm_100a batched small-FFT kernels.
+//
+// Replaces the reference's configure_* / generate_* pair
+// (reference: include/bbfft/detail/generator_impl.hpp:26-107,
+//  src/base/generator/small_batch_fft.cpp:15-110, src/base/generator/factor2_slm_fft.cpp:16-116):
+// given a 1d bbfft configuration it chooses the stage radices, the thread layout, the shared
+// memory layout, builds the twiddle table and emits the NVRTC/nvcc "stub" that instantiates
+// bbk::fft1d<C> from kernels/bbfft_kernels.cuh.
+#ifndef BBFFT_CUDA_PLANNER_HPP
+#define BBFFT_CUDA_PLANNER_HPP
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace bbfft::cuda {
+
+enum kernel_mode : int { k_c2c = 0, k_r2c_half = 1, k_c2r_half = 2, k_r2c_double = 3, k_c2r_double = 4 };
+
+struct problem_1d {
+    int fp = 4;            // bytes per real: 4 | 8   (bbfft::precision)
+    int dir = -1;          // -1 forward, +1 backward (bbfft::direction)
+    int type = 0;          // 0 c2c, 1 r2c, 2 c2r     (bbfft::transform_type)
+    std::uint64_t M = 1, N = 1, K = 1;
+    std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1; // strides[1], strides[2]
+    std::string cb_source, cb_load, cb_store;       // CUDA C callbacks (may be empty)
+};
+
+struct device_props {
+    int sm_count = 148;
+    int max_threads_per_block = 1024;
+    std::size_t max_smem_per_block = 227 * 1024;
+    std::size_t smem_per_sm = 228 * 1024;
+    int regs_per_sm = 65536;
+    int cc_major = 10, cc_minor = 0;
+};
+
+struct kernel_params {
+    int fp = 4, dir = -1, mode = k_c2c;
+    int N = 1;     // length of the complex FFT the stages run
+    int nreal = 1; // user-visible N
+    int L = 1;
+    int radix[4] = {1, 1, 1, 1};
+    int T = 1, ML = 1, BH = 1;
+    bool klanes = false, load_staged = false, store_staged = false;
+    std::uint64_t M = 1;
+    std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1;
+    int LL = 1, PADK = 0, ROW = 1;
+    std::size_t smem_bytes = 0;
+    int threads = 1;
+    int min_blocks = 1;
+    std::string cb_load, cb_store;
+
+    int batch_per_cta() const { return ML * BH; }
+    // number of CTAs for K slices
+    std::uint64_t grid(std::uint64_t K) const;
+    // k slices consumed per CTA (for odd-N real transforms a slice pair counts as one unit)
+    std::uint64_t k_per_cta() const;
+};
+
+struct kernel_plan {
+    kernel_params p;
+    std::string identifier;      // cache key / kernel name
+    std::string source;          // stub (includes "bbfft_kernels.cuh")
+    std::vector<double> twiddle; // interleaved re,im in double; narrowed by the caller
+    bool inplace_unsupported = false;
+};
+
+// Tuning overrides, "key=value,key=value" (keys: R=8x8, T, ML, BH, LD, ST, PADK, ROW, KL).
+// Used by the auto-tuner and the tests; empty string = heuristics.
+kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
+                           std::string const &tune = std::string());
+
+std::string emit_stub(kernel_params const &p, std::string const &identifier,
+                      std::string const &cb_source);
+std::string make_identifier(kernel_params const &p);
+std::vector<double> make_twiddles(kernel_params const &p);
+
+// integer helpers (pinned by tests; semantics of reference src/base/prime_factorization.cpp)
+std::vector<int> prime_factors(int n);
+bool radix_supported(int r);
+
+} // namespace bbfft::cuda
+
+#endif

@@ -1,0 +1,316 @@
+// runtime.cpp -- see runtime.hpp.
+#include "runtime.hpp"
+
+#include "bbfft/cuda/device.hpp"
+#include "bbfft/cuda/error.hpp"
+#include "bbfft/cuda/make_plan.hpp"
+#include "bbfft/cuda/online_compiler.hpp"
+
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+#include <sstream>
+
+namespace bbfft::cuda {
+
+void throw_on_error(int cuda_error, char const *file, int line) {
+    if (cuda_error != 0) {
+        std::ostringstream os;
+        os << file << ":" << line << ": CUDA error " << cuda_error << " ("
+           << cudaGetErrorName(static_cast<cudaError_t>(cuda_error))
+           << "): " << cudaGetErrorString(static_cast<cudaError_t>(cuda_error));
+        throw error(os.str(), cuda_error);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NVRTC, loaded lazily
+// ------------------------------------------------------------------------------------------
+namespace {
+struct nvrtc_api {
+    void *lib = nullptr;
+    int (*create)(void **prog, const char *src, const char *name, int nh, const char *const *headers,
+                  const char *const *include_names) = nullptr;
+    int (*compile)(void *prog, int nopt, const char *const *opts) = nullptr;
+    int (*destroy)(void **prog) = nullptr;
+    int (*cubin_size)(void *prog, size_t *sz) = nullptr;
+    int (*cubin)(void *prog, char *out) = nullptr;
+    int (*log_size)(void *prog, size_t *sz) = nullptr;
+    int (*log)(void *prog, char *out) = nullptr;
+    const char *(*error_string)(int) = nullptr;
+};
+
+nvrtc_api &nvrtc() {
+    static nvrtc_api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (auto n : names) {
+            a.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) return;
+        auto sym = [&](const char *s) { return dlsym(a.lib, s); };
+        a.create = reinterpret_cast<decltype(a.create)>(sym("nvrtcCreateProgram"));
+        a.compile = reinterpret_cast<decltype(a.compile)>(sym("nvrtcCompileProgram"));
+        a.destroy = reinterpret_cast<decltype(a.destroy)>(sym("nvrtcDestroyProgram"));
+        a.cubin_size = reinterpret_cast<decltype(a.cubin_size)>(sym("nvrtcGetCUBINSize"));
+        a.cubin = reinterpret_cast<decltype(a.cubin)>(sym("nvrtcGetCUBIN"));
+        a.log_size = reinterpret_cast<decltype(a.log_size)>(sym("nvrtcGetProgramLogSize"));
+        a.log = reinterpret_cast<decltype(a.log)>(sym("nvrtcGetProgramLog"));
+        a.error_string = reinterpret_cast<decltype(a.error_string)>(sym("nvrtcGetErrorString"));
+    });
+    if (!a.lib || !a.create || !a.compile || !a.cubin) {
+        throw error("bbfft-cuda: NVRTC (libnvrtc.so.12) could not be loaded; it is required to "
+                    "build FFT kernels at plan creation",
+                    -1);
+    }
+    return a;
+}
+} // namespace
+
+std::vector<std::uint8_t> nvrtc_compile(std::string const &source, std::string const &arch,
+                                        std::vector<std::string> const &extra_options) {
+    auto &rt = nvrtc();
+    void *prog = nullptr;
+    const char *headers[] = {kernel_header_text()};
+    const char *names[] = {"bbfft_kernels.cuh"};
+    int rc = rt.create(&prog, source.c_str(), "bbfft_kernel.cu", 1, headers, names);
+    if (rc != 0) {
+        throw error(std::string("nvrtcCreateProgram failed: ") + rt.error_string(rc), rc);
+    }
+    std::vector<std::string> opts = {"--gpu-architecture=" + arch, "-std=c++17", "-lineinfo",
+                                     "-default-device"};
+    for (auto const &o : extra_options) opts.push_back(o);
+    std::vector<const char *> copts;
+    for (auto const &o : opts) copts.push_back(o.c_str());
+    rc = rt.compile(prog, int(copts.size()), copts.data());
+    if (rc != 0) {
+        std::string log;
+        size_t sz = 0;
+        if (rt.log_size(prog, &sz) == 0 && sz > 1) {
+            log.resize(sz);
+            rt.log(prog, log.data());
+        }
+        rt.destroy(&prog);
+        throw error(std::string("bbfft-cuda: kernel compilation failed (") + rt.error_string(rc) +
+                        ")\n" + log,
+                    rc);
+    }
+    size_t sz = 0;
+    rc = rt.cubin_size(prog, &sz);
+    std::vector<std::uint8_t> bin(sz);
+    if (rc == 0 && sz > 0) rc = rt.cubin(prog, reinterpret_cast<char *>(bin.data()));
+    rt.destroy(&prog);
+    if (rc != 0 || sz == 0) {
+        throw error("bbfft-cuda: nvrtcGetCUBIN failed", rc);
+    }
+    return bin;
+}
+
+auto compile_to_native(std::string const &source, std::string const &arch,
+                       std::vector<std::string> const &options) -> std::vector<std::uint8_t> {
+    return nvrtc_compile(source, arch, options);
+}
+
+// ------------------------------------------------------------------------------------------
+// modules
+// ------------------------------------------------------------------------------------------
+module_handle_t load_module_image(void const *image) {
+    cudaLibrary_t lib = nullptr;
+    BBFFT_CUDA_CHECK(cudaLibraryLoadData(&lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0));
+    return reinterpret_cast<module_handle_t>(lib);
+}
+
+void unload_module(module_handle_t mod) {
+    if (mod) cudaLibraryUnload(reinterpret_cast<cudaLibrary_t>(mod));
+}
+
+auto make_shared_handle(module_handle_t mod) -> shared_handle<module_handle_t> {
+    return shared_handle<module_handle_t>(mod, &unload_module);
+}
+
+auto build_native_module(std::string const &source, int device, std::vector<std::string> const &options)
+    -> module_handle_t {
+    BBFFT_CUDA_CHECK(cudaSetDevice(device));
+    api a(nullptr, device);
+    auto bin = nvrtc_compile(source, a.arch(), options);
+    return load_module_image(bin.data());
+}
+
+auto build_native_module(std::uint8_t const *binary, std::size_t, module_format format, int device)
+    -> module_handle_t {
+    if (format != module_format::native) {
+        throw bad_configuration("the CUDA backend loads native modules (cubin/fatbin) only");
+    }
+    BBFFT_CUDA_CHECK(cudaSetDevice(device));
+    return load_module_image(binary);
+}
+
+auto get_kernel_names(module_handle_t mod) -> std::vector<std::string> {
+    auto lib = reinterpret_cast<cudaLibrary_t>(mod);
+    unsigned int count = 0;
+    BBFFT_CUDA_CHECK(cudaLibraryGetKernelCount(&count, lib));
+    std::vector<cudaKernel_t> kernels(count);
+    if (count) BBFFT_CUDA_CHECK(cudaLibraryEnumerateKernels(kernels.data(), count, lib));
+    std::vector<std::string> names;
+    for (auto k : kernels) {
+        // the runtime has no name query for cudaKernel_t; go through the driver entry point
+        using fn_t = int (*)(const char **, void *);
+        static fn_t get_name = [] {
+            void *f = nullptr;
+            cudaDriverEntryPointQueryResult st;
+            if (cudaGetDriverEntryPoint("cuKernelGetName", &f, cudaEnableDefault, &st) != cudaSuccess) f = nullptr;
+            return reinterpret_cast<fn_t>(f);
+        }();
+        const char *nm = nullptr;
+        if (get_name && get_name(&nm, k) == 0 && nm) names.emplace_back(nm);
+    }
+    return names;
+}
+
+aot_module create_aot_module(std::uint8_t const *binary, std::size_t binary_size, module_format format,
+                             int device) {
+    aot_module m;
+    auto handle = build_native_module(binary, binary_size, format, device);
+    m.mod = make_shared_handle(handle);
+    for (auto &n : get_kernel_names(handle)) m.kernel_names.insert(n);
+    m.device_id = query_device_id(device);
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------
+device_props query_device_props(int device) {
+    cudaDeviceProp p;
+    BBFFT_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    device_props d;
+    d.sm_count = p.multiProcessorCount;
+    d.max_threads_per_block = p.maxThreadsPerBlock;
+    d.max_smem_per_block = p.sharedMemPerBlockOptin;
+    d.smem_per_sm = p.sharedMemPerMultiprocessor;
+    d.regs_per_sm = p.regsPerMultiprocessor;
+    d.cc_major = p.major;
+    d.cc_minor = p.minor;
+    return d;
+}
+
+std::uint64_t query_device_id(int device) {
+    cudaDeviceProp p;
+    BBFFT_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    // FNV-1a over uuid + compute capability: same physical device -> same id
+    std::uint64_t h = 1469598103934665603ull;
+    auto mix = [&](unsigned char c) {
+        h ^= c;
+        h *= 1099511628211ull;
+    };
+    for (unsigned char c : p.uuid.bytes) mix(c);
+    mix(static_cast<unsigned char>(p.major));
+    mix(static_cast<unsigned char>(p.minor));
+    return h;
+}
+
+} // namespace bbfft::cuda
+
+namespace bbfft {
+auto get_device_info(int device) -> device_info {
+    auto p = cuda::query_device_props(device);
+    device_info info;
+    info.max_work_group_size = std::size_t(p.max_threads_per_block);
+    info.subgroup_sizes = {32};
+    info.local_memory_size = p.max_smem_per_block;
+    info.type = device_type::gpu;
+    return info;
+}
+auto get_device_id(int device) -> std::uint64_t { return cuda::query_device_id(device); }
+} // namespace bbfft
+
+namespace bbfft::cuda {
+
+// ------------------------------------------------------------------------------------------
+// event
+// ------------------------------------------------------------------------------------------
+event::event(cudaStream_t stream) {
+    cudaEvent_t e = nullptr;
+    BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_ = std::shared_ptr<cudaEvent_t>(new cudaEvent_t(e), [](cudaEvent_t *p) {
+        if (*p) cudaEventDestroy(*p);
+        delete p;
+    });
+    BBFFT_CUDA_CHECK(cudaEventRecord(e, stream));
+}
+
+void event::wait() const {
+    if (ev_) BBFFT_CUDA_CHECK(cudaEventSynchronize(*ev_));
+}
+
+// ------------------------------------------------------------------------------------------
+// api
+// ------------------------------------------------------------------------------------------
+api::api(cudaStream_t stream, int device) : stream_(stream), device_(device) {
+    if (device_ < 0) BBFFT_CUDA_CHECK(cudaGetDevice(&device_));
+    props_ = query_device_props(device_);
+    device_id_ = query_device_id(device_);
+}
+
+device_info api::info() const { return get_device_info(device_); }
+
+std::string api::arch() const {
+    std::ostringstream os;
+    os << "sm_" << props_.cc_major << props_.cc_minor;
+    if (props_.cc_major >= 9) os << "a";
+    return os.str();
+}
+
+shared_handle<module_handle_t> api::build_module(std::string const &source) const {
+    auto bin = nvrtc_compile(source, arch(), {});
+    return make_shared_handle(load_module_image(bin.data()));
+}
+
+cudaKernel_t api::create_kernel(module_handle_t mod, std::string const &name, std::size_t smem_bytes) const {
+    cudaKernel_t k = nullptr;
+    BBFFT_CUDA_CHECK(cudaLibraryGetKernel(&k, reinterpret_cast<cudaLibrary_t>(mod), name.c_str()));
+    if (smem_bytes > 48 * 1024) {
+        BBFFT_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void *>(k),
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+    }
+    return k;
+}
+
+void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
+                        kernel_args const &args, cudaStream_t stream) const {
+    if (grid == 0) return;
+    if (grid > 0x7fffffffull) {
+        throw bad_configuration("bbfft-cuda: batch too large for one launch");
+    }
+    kernel_args a = args;
+    void *params[] = {&a};
+    BBFFT_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void *>(k), dim3(unsigned(grid)),
+                                      dim3(unsigned(threads)), params, smem_bytes, stream));
+}
+
+void *api::create_device_buffer(std::size_t bytes) const {
+    void *p = nullptr;
+    BBFFT_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+    return p;
+}
+
+void api::release_buffer(void *ptr) const {
+    if (ptr) cudaFree(ptr);
+}
+
+void *api::create_twiddle_table(std::vector<double> const &tw, int fp) const {
+    void *dev = create_device_buffer(tw.size() * std::size_t(fp));
+    if (fp == 4) {
+        std::vector<float> f(tw.begin(), tw.end());
+        BBFFT_CUDA_CHECK(cudaMemcpy(dev, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    } else {
+        BBFFT_CUDA_CHECK(cudaMemcpy(dev, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return dev;
+}
+
+} // namespace bbfft::cuda

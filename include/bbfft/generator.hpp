@@ -1,0 +1,5 @@
+// bbfft/generator.hpp -- same include name as the reference; everything lives in bbfft/api.hpp.
+#ifndef BBFFT_FWD_GENERATOR_HPP
+#define BBFFT_FWD_GENERATOR_HPP
+#include "bbfft/api.hpp"
+#endif

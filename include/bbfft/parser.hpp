@@ -1,0 +1,5 @@
+// bbfft/parser.hpp -- same include name as the reference; everything lives in bbfft/api.hpp.
+#ifndef BBFFT_FWD_PARSER_HPP
+#define BBFFT_FWD_PARSER_HPP
+#include "bbfft/api.hpp"
+#endif

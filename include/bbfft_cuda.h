@@ -1,0 +1,120 @@
+/* bbfft_cuda.h -- C ABI of the B200 (sm_100a) backend of the Double-Batched FFT Library.
+ *
+ * This is the drop-in boundary for the batched small-FFT hot path: plain pointers and sizes,
+ * no C++ or torch types.  The reference has no C ABI (its boundary is the C++ `Api` policy and
+ * the virtual plan_impl::execute); each entry point below names the reference interface it
+ * stands in for.  File:line citations are into intel/double-batched-fft-library v0.5.1.
+ *
+ * Status codes: 0 success, 1 error, 2 bad configuration (bbfft::bad_configuration),
+ * 3 CUDA / NVRTC failure.  bbfft_cuda_last_error() returns the message of the last failure on
+ * the calling thread.
+ */
+#ifndef BBFFT_CUDA_H
+#define BBFFT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBFFT_CUDA_MAX_TENSOR_DIM 5
+
+enum { BBFFT_CUDA_OK = 0, BBFFT_CUDA_ERROR = 1, BBFFT_CUDA_BAD_CONFIGURATION = 2, BBFFT_CUDA_DEVICE_ERROR = 3 };
+
+/* POD mirror of bbfft::configuration (include/bbfft/configuration.hpp:151-192).
+ * shape = {M, N_1, ..., N_dim, K}; strides in elements of the tensor's own type; fp = 4 | 8
+ * (bbfft::precision); dir = -1 | +1 (bbfft::direction); type = 0 c2c, 1 r2c, 2 c2r
+ * (bbfft::transform_type).  Callback fields mirror bbfft::user_module
+ * (include/bbfft/user_module.hpp:24-37); cb_language 0 = OpenCL-C subset, 1 = CUDA C++. */
+typedef struct bbfft_cuda_config {
+    unsigned dim;
+    size_t shape[BBFFT_CUDA_MAX_TENSOR_DIM];
+    int fp;
+    int dir;
+    int type;
+    size_t istride[BBFFT_CUDA_MAX_TENSOR_DIM];
+    size_t ostride[BBFFT_CUDA_MAX_TENSOR_DIM];
+    const char *cb_source;
+    size_t cb_length;
+    const char *cb_load;
+    const char *cb_store;
+    int cb_language;
+} bbfft_cuda_config;
+
+typedef struct bbfft_cuda_plan_s *bbfft_cuda_plan_t;
+typedef struct bbfft_cuda_cache_s *bbfft_cuda_cache_t;
+
+const char *bbfft_cuda_last_error(void);
+
+/* bbfft::default_istride / default_ostride (src/base/configuration.cpp:24-56). */
+int bbfft_cuda_default_strides(const bbfft_cuda_config *cfg, int inplace, size_t *istride, size_t *ostride);
+/* bbfft::parse_fft_descriptor (src/base/parser.cpp:59-211) and configuration::to_string
+ * (src/base/configuration.cpp:69-160). */
+int bbfft_cuda_parse_descriptor(const char *descriptor, bbfft_cuda_config *cfg);
+int bbfft_cuda_to_descriptor(const bbfft_cuda_config *cfg, char *buffer, size_t buffer_size);
+
+/* bbfft::jit_cache_all (include/bbfft/jit_cache_all.hpp:20-37): share compiled kernels between
+ * plans.  A NULL cache is allowed everywhere. */
+int bbfft_cuda_cache_create(bbfft_cuda_cache_t *cache);
+int bbfft_cuda_cache_destroy(bbfft_cuda_cache_t cache);
+int bbfft_cuda_cache_size(bbfft_cuda_cache_t cache);
+
+/* bbfft::make_plan(cfg, queue, cache) (include/bbfft/sycl/make_plan.hpp:27-41, src/sycl/plan.cpp:16-24).
+ * `stream` is a cudaStream_t (NULL = default stream); device < 0 = current device. */
+int bbfft_cuda_plan_create(bbfft_cuda_plan_t *plan, const bbfft_cuda_config *cfg, void *stream, int device,
+                           bbfft_cuda_cache_t cache);
+/* Same, with planner overrides ("R=8x8,T=8,BH=2,..."; used by the auto-tuner). 1d only. */
+int bbfft_cuda_plan_create_tuned(bbfft_cuda_plan_t *plan, const bbfft_cuda_config *cfg, void *stream,
+                                 int device, bbfft_cuda_cache_t cache, const char *tune);
+/* plan::execute(in, out) (include/bbfft/plan.hpp:77-131): asynchronous, stream ordered;
+ * in == out selects the in-place transform.  Pointers are device (or managed / pinned) memory. */
+int bbfft_cuda_plan_execute(bbfft_cuda_plan_t plan, const void *in, void *out);
+int bbfft_cuda_plan_execute_on(bbfft_cuda_plan_t plan, const void *in, void *out, void *stream);
+/* Host-buffer convenience: H2D copy of `in_bytes`, execute, D2H copy of `out_bytes`, then
+ * synchronise.  Device staging buffers are owned by the plan.  host_in == host_out runs in place. */
+int bbfft_cuda_plan_execute_host(bbfft_cuda_plan_t plan, const void *host_in, size_t in_bytes, void *host_out,
+                                 size_t out_bytes);
+int bbfft_cuda_plan_destroy(bbfft_cuda_plan_t plan);
+/* Introspection: kernels launched per execute and their identifiers (cache keys,
+ * reference: src/base/generator/small_batch_fft.cpp:60-80). */
+int bbfft_cuda_plan_num_kernels(bbfft_cuda_plan_t plan);
+const char *bbfft_cuda_plan_kernel_name(bbfft_cuda_plan_t plan, int index);
+
+/* Device-free planning and code generation (bbfft::generate_fft_kernels,
+ * include/bbfft/generator.hpp:22-36, src/base/generator.cpp:16-25). */
+typedef struct bbfft_cuda_kernel_desc {
+    char *identifier;
+    char *source;          /* CUDA C++ stub; #includes "bbfft_kernels.cuh" */
+    double *twiddle;       /* interleaved re, im */
+    size_t twiddle_len;    /* number of doubles */
+    uint64_t grid;
+    int threads;
+    size_t smem_bytes;
+    int inplace_unsupported;
+    int fp;
+    int n_stages;
+    int radix[4];
+    int threads_per_transform;
+    int batch_lanes;
+    int batch_high;
+    int load_staged;
+    int store_staged;
+} bbfft_cuda_kernel_desc;
+int bbfft_cuda_describe(const bbfft_cuda_config *cfg, const char *tune, bbfft_cuda_kernel_desc *desc);
+void bbfft_cuda_desc_free(bbfft_cuda_kernel_desc *desc);
+/* All kernels (1d..3d) of a list of configurations as one translation unit; *source is
+ * malloc'ed, *names is a malloc'ed '\n'-separated list. */
+int bbfft_cuda_generate_kernels(const bbfft_cuda_config *cfgs, size_t n, char **source, char **names);
+/* Text of the device header the stubs include (for offline nvcc builds and the CPU emulator). */
+const char *bbfft_cuda_kernel_header(void);
+/* NVRTC: CUDA C++ -> cubin for `arch` (e.g. "sm_100a").  Needs no GPU.  *binary is malloc'ed. */
+int bbfft_cuda_compile(const char *source, const char *arch, uint8_t **binary, size_t *binary_size);
+void bbfft_cuda_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BBFFT_CUDA_H */

@@ -1,0 +1,64 @@
+"""tests/emu/emu.py -- TEST INFRASTRUCTURE ONLY.
+
+Runs a planned bbfft CUDA kernel on the CPU: the stub the planner generated and the device
+header are compiled with g++ (-DBBFFT_EMU) against cuda_emu.hpp and executed one fiber per
+CUDA thread by emu_runner.cpp.  This lets the CPU-only test tier check every index map of the
+real kernel source against the oracle.  Never used by the product path.
+"""
+import ctypes as C
+import hashlib
+import importlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_KERNELS = os.path.join(_ROOT, "double-batched-fft-library_b200", "csrc", "kernels")
+_CACHE = os.path.join(tempfile.gettempdir(), "bbfft_emu_cache_%d" % os.getuid())
+
+pkg = importlib.import_module("double-batched-fft-library_b200")
+
+
+class Args(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("out", C.c_void_p), ("tw", C.c_void_p), ("K", C.c_ulonglong),
+                ("M", C.c_ulonglong), ("is1", C.c_longlong), ("is2", C.c_longlong), ("os1", C.c_longlong),
+                ("os2", C.c_longlong)]
+
+
+def _compile(desc):
+    os.makedirs(_CACHE, exist_ok=True)
+    hdr = open(os.path.join(_KERNELS, "bbfft_kernels.cuh")).read()
+    runner = open(os.path.join(_HERE, "emu_runner.cpp")).read()
+    key = hashlib.sha1((desc["source"] + hdr + runner).encode()).hexdigest()[:20]
+    so = os.path.join(_CACHE, key + ".so")
+    if not os.path.exists(so):
+        stub = os.path.join(_CACHE, key + ".cpp")
+        with open(stub, "w") as f:
+            f.write(desc["source"])
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DBBFFT_EMU",
+               "-DBBFFT_EMU_KERNEL=" + desc["identifier"], "-I" + _HERE, "-I" + _KERNELS, "-include",
+               os.path.join(_HERE, "cuda_emu.hpp"), stub, os.path.join(_HERE, "emu_runner.cpp"), "-o",
+               so + ".tmp"]
+        subprocess.check_call(cmd)
+        os.replace(so + ".tmp", so)
+    return C.CDLL(so)
+
+
+def run(cfg, inp, out=None, tune=""):
+    """Execute the planned kernel for 1d `cfg` on numpy buffers (out=None -> in place)."""
+    desc = pkg.describe(cfg, tune)
+    lib = _compile(desc)
+    lib.emu_launch.argtypes = [C.POINTER(Args), C.c_ulonglong, C.c_int, C.c_ulong]
+    tw = desc["twiddle"].astype(np.float32 if desc["fp"] == 4 else np.float64)
+    if out is None:
+        out = inp
+    a = Args(inp.ctypes.data, out.ctypes.data, tw.ctypes.data, cfg.shape[2], cfg.shape[0], cfg.istride[1],
+             cfg.istride[2], cfg.ostride[1], cfg.ostride[2])
+    rc = lib.emu_launch(C.byref(a), desc["grid"], desc["threads"], desc["smem_bytes"])
+    if rc != 0:
+        raise RuntimeError("emulated kernel failed (rc=%d): divergent barriers" % rc)
+    return out, desc

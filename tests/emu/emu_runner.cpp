@@ -1,0 +1,83 @@
+// tests/emu/emu_runner.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiled together with one generated stub (-DBBFFT_EMU -DBBFFT_EMU_KERNEL=<identifier>
+// -include cuda_emu.hpp) into a shared object; emu_launch() runs the kernel grid on the host.
+#include "cuda_emu.hpp"
+#include "bbfft_kernels.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <ucontext.h>
+#include <vector>
+
+extern "C" void BBFFT_EMU_KERNEL(bbk::args a);
+
+namespace bbfft_emu {
+thread_local thread_ctx *current = nullptr;
+}
+
+namespace {
+constexpr std::size_t stack_bytes = 256 * 1024;
+struct fiber {
+    ucontext_t uc;
+    bbfft_emu::thread_ctx ctx;
+    bool done = false;
+    char *stack = nullptr;
+};
+thread_local ucontext_t sched_uc;
+thread_local fiber *running = nullptr;
+thread_local bbk::args *launch_args = nullptr;
+
+void yield_to_sched(bbfft_emu::thread_ctx *) {
+    fiber *f = running;
+    swapcontext(&f->uc, &sched_uc);
+}
+void fiber_main() {
+    fiber *f = running;
+    bbfft_emu::current = &f->ctx;
+    BBFFT_EMU_KERNEL(*launch_args);
+    f->done = true;
+    swapcontext(&f->uc, &sched_uc);
+}
+} // namespace
+
+extern "C" int emu_launch(bbk::args *a, unsigned long long grid, int threads, unsigned long smem_bytes) {
+    launch_args = a;
+    std::vector<fiber> fibers(threads);
+    for (auto &f : fibers) {
+        f.stack = static_cast<char *>(std::malloc(stack_bytes));
+    }
+    std::vector<unsigned char> smem(smem_bytes + 64);
+    for (unsigned long long bid = 0; bid < grid; ++bid) {
+        std::memset(smem.data(), 0xcd, smem.size());
+        for (int t = 0; t < threads; ++t) {
+            fiber &f = fibers[t];
+            f.done = false;
+            f.ctx = {t, bid, smem.data(), yield_to_sched};
+            getcontext(&f.uc);
+            f.uc.uc_stack.ss_sp = f.stack;
+            f.uc.uc_stack.ss_size = stack_bytes;
+            f.uc.uc_link = nullptr;
+            makecontext(&f.uc, fiber_main, 0);
+        }
+        for (;;) {
+            int done = 0;
+            for (int t = 0; t < threads; ++t) {
+                fiber &f = fibers[t];
+                if (!f.done) {
+                    running = &f;
+                    bbfft_emu::current = &f.ctx;
+                    swapcontext(&sched_uc, &f.uc);
+                }
+                if (f.done) ++done;
+            }
+            if (done == threads) break;
+            if (done != 0) {
+                // some threads returned while others wait at a barrier: CUDA would hang
+                for (auto &f : fibers) std::free(f.stack);
+                return 2;
+            }
+        }
+    }
+    for (auto &f : fibers) std::free(f.stack);
+    return 0;
+}
