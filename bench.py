@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batched small-FFT path.
+
+Workload (BASELINE.json configs[1]): 1d c2c, fp32 + fp64, double-batched M=16, N = the 105
+seven-smooth sizes in [2,512] (the reference's own sweep, tools/powers.py -p 4 2 512), K sized so
+that every input tensor is ~1 GiB (benchmark/test.hpp:18-30), out-of-place, forward.  One "step"
+is one execute of every (precision, N) plan of the sweep: 210 kernel launches, ~210 GiB of
+input streamed.  Metric: aggregate GFLOP/s under the reference's 5*N*log2(N) convention
+(benchmark/adapter.hpp:51) plus the achieved HBM GB/s (2*N*sizeof(complex) bytes per transform,
+benchmark/adapter.hpp:52).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1: launched by torchrun, one rank per GPU; every rank owns its own contiguous K slab of the
+same size (weak scaling), no collective on the data path; the timed
+region is bracketed by barriers and the max over ranks is reported.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "double-batched-fft-library_b200"
+
+M_BATCH = 16
+TENSOR_BYTES = 1 << 30
+
+
+def sweep_sizes():
+    aot = importlib.import_module(PKG + ".aot")
+    return aot.smooth_sizes()
+
+
+def flops_c2c(n, transforms):
+    return 5.0 * n * math.log2(n) * transforms
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's generated kernels under the host emulator (oracle/_ref), all cores
+# ------------------------------------------------------------------------------------------------
+REF_SAMPLE = [(4, 2, 4096), (4, 8, 2048), (4, 27, 512), (4, 64, 384), (4, 105, 192), (4, 256, 96), (4, 512, 48),
+              (8, 8, 2048), (8, 64, 384), (8, 105, 192), (8, 512, 48)]
+
+
+def run_reference_sample(steps, warmup, threads):
+    """Returns (gflops, gbs, seconds_per_step, kind, sample description)."""
+    import numpy as np
+    from oracle import oracle, refemu
+    kind = "reference" if refemu.available() else "port"
+    rng = np.random.default_rng(0)
+    work = []
+    for fp, n, k in REF_SAMPLE:
+        dt = np.complex64 if fp == 4 else np.complex128
+        x = (rng.standard_normal((k, n, M_BATCH)) + 1j * rng.standard_normal((k, n, M_BATCH))).astype(dt)
+        y = np.empty_like(x)
+        if kind == "reference":
+            refemu.set_threads(threads)
+            plan = refemu.Plan(refemu.make_config(1, [M_BATCH, n, k], fp, -1, 0, inplace=False))
+            fn = (lambda p=plan, a=x, b=y: p.execute(a, b))
+        else:
+            cfg = oracle.make_config(1, [M_BATCH, n, k], fp, -1, 0, inplace=False)
+            fn = (lambda c=cfg, a=x, b=y: oracle.bbfft(c, a, b))
+        work.append((fn, flops_c2c(n, M_BATCH * k), 2.0 * M_BATCH * n * k * 2 * fp))
+    for _ in range(warmup):
+        for fn, _, _ in work:
+            fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for fn, _, _ in work:
+            fn()
+    dt = (time.perf_counter() - t0) / steps
+    fl = sum(w[1] for w in work)
+    by = sum(w[2] for w in work)
+    sample = "c2c M=16 (fp,N,K) in %s: the sweep's shapes with K cut to a CPU-sized batch" % (REF_SAMPLE,)
+    return fl / dt * 1e-9, by / dt * 1e-9, dt, kind, sample
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    warmup = max(1, min(args.warmup, 3))
+    gf, gbs, dt, kind, sample = run_reference_sample(steps, warmup, threads)
+    line = {
+        "impl": "reference",
+        "metric": "c2c GFLOP/s (5N*log2N), 1d double-batched sweep N=2..512",
+        "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "gbs": gbs,
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": "1d c2c fp32+fp64 sweep, 105 seven-smooth N in [2,512], M=16, K=1GiB/(16*N*sizeof(complex)) per GPU, out-of-place, forward",
+            "M": M_BATCH, "tensor_bytes_per_gpu": TENSOR_BYTES, "n_sizes": len(sweep_sizes()),
+            "l2": "inputs_larger_than_l2 (2 GiB streamed per launch)", "parallelism": "k-sharded x%d, no collective" % gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--per-size", default="", help="write the per-size table to this CSV")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    pkg = importlib.import_module(PKG)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    sizes = sweep_sizes()
+    # resident synthetic inputs: one 1 GiB input + 1 GiB output buffer per precision
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    bufs = {}
+    for fp, rdt in ((4, torch.float32), (8, torch.float64)):
+        n_real = TENSOR_BYTES // fp
+        x = torch.empty(n_real, dtype=rdt, device=dev)
+        x.uniform_(0.0, 1.0, generator=gen)
+        y = torch.empty(n_real, dtype=rdt, device=dev)
+        bufs[fp] = (x, y)
+    plans = []
+    cache = pkg.Cache()
+    for fp in (4, 8):
+        for n in sizes:
+            k = max(1, TENSOR_BYTES // (M_BATCH * n * 2 * fp))
+            cfg = pkg.make_config(1, [M_BATCH, n, k], fp, pkg.FORWARD, pkg.C2C, inplace=False)
+            plan = pkg.Plan(cfg, stream=stream, device=local_rank, cache=cache)
+            plans.append((fp, n, k, plan))
+    launches_per_step = sum(p.launches_per_execute for _, _, _, p in plans)
+
+    def run_step(events=None):
+        for i, (fp, n, k, plan) in enumerate(plans):
+            x, y = bufs[fp]
+            if events is not None:
+                events[i][0].record()
+            plan.execute(x, y)
+            if events is not None:
+                events[i][1].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        run_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    per = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plans]
+           for _ in range(steps)]
+    barrier()
+    ev0.record()
+    for s in range(steps):
+        run_step(per[s])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = ev0.elapsed_time(ev1) * 1e-3
+    if world > 1:
+        t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+
+    total_flops = sum(flops_c2c(n, M_BATCH * k) for _, n, k, _ in plans) * world
+    total_bytes = sum(2.0 * M_BATCH * n * k * 2 * fp for fp, n, k, _ in plans) * world
+    per_step = elapsed / steps
+    value = total_flops / per_step * 1e-9
+    gbs = total_bytes / per_step * 1e-9
+
+    # per-launch kernel durations (CUDA events on the launching stream), this rank
+    rows = []
+    kernel_time = 0.0
+    for i, (fp, n, k, plan) in enumerate(plans):
+        ts = sorted(per[s][i][0].elapsed_time(per[s][i][1]) * 1e-3 for s in range(steps))
+        avg = sum(ts) / len(ts)
+        kernel_time += avg
+        b = 2.0 * M_BATCH * n * k * 2 * fp
+        rows.append((fp, n, k, avg, b / avg * 1e-9, flops_c2c(n, M_BATCH * k) / avg * 1e-9, plan.kernel_names[0]))
+    peak, peak_src = peak_hbm()
+    fracs = sorted(r[4] / peak for r in rows)
+    worst = min(rows, key=lambda r: r[4])
+    bytes_rank = total_bytes / world
+    roofline = {
+        "bound": "hbm", "achieved": bytes_rank / kernel_time * 1e-9, "peak": peak, "unit": "GB/s",
+        "frac": bytes_rank / kernel_time * 1e-9 / peak, "traffic": None, "peak_source": peak_src,
+        "kernel": "bbk::fft1d<C> (all 210 instantiations of the sweep, per-launch CUDA events)",
+        "algorithmic_bytes_per_launch": "2*N*sizeof(complex)*M*K = 2 GiB",
+        "per_size_frac": {"min": fracs[0], "median": fracs[len(fracs) // 2], "max": fracs[-1],
+                          "n_below_0.8": sum(1 for f in fracs if f < 0.8)},
+        "worst": {"fp": worst[0], "N": worst[1], "GBs": worst[4], "kernel": worst[6]},
+    }
+    if args.per_size and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.per_size)), exist_ok=True)
+        with open(args.per_size, "w") as f:
+            f.write("fp,N,K,time_us,GBs,frac_of_peak,GFLOPs,kernel\n")
+            for r in rows:
+                f.write("%d,%d,%d,%.2f,%.1f,%.4f,%.1f,%s\n" % (r[0], r[1], r[2], r[3] * 1e6, r[4], r[4] / peak, r[5], r[6]))
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if args.e2e_steps > 0:
+        hin = torch.empty(TENSOR_BYTES, dtype=torch.uint8).pin_memory()
+        hout = torch.empty(TENSOR_BYTES, dtype=torch.uint8).pin_memory()
+        hin.view(torch.float32).uniform_(0.0, 1.0)
+        hin64 = torch.empty(TENSOR_BYTES, dtype=torch.uint8).pin_memory()
+        hin64.view(torch.float64).uniform_(0.0, 1.0)
+        h2d = d2h = 0
+        for fp, n, k, plan in plans:
+            nb = M_BATCH * n * k * 2 * fp
+            h2d += nb
+            d2h += nb
+
+        def e2e_step():
+            for fp, n, k, plan in plans:
+                nb = M_BATCH * n * k * 2 * fp
+                src = hin if fp == 4 else hin64
+                plan.execute_host(src[:nb], hout[:nb])
+
+        barrier()
+        e2e_step_count = args.e2e_steps
+        t0 = time.perf_counter()
+        for _ in range(e2e_step_count):
+            e2e_step()
+        barrier()
+        t_e2e = (time.perf_counter() - t0) / e2e_step_count
+        if world > 1:
+            t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": total_flops / t_e2e * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3, "steps": e2e_step_count,
+               "api": "bbfft_cuda_plan_execute_host (pinned host buffers, H2D + kernel + D2H per plan)"}
+        del hin, hout, hin64
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                gf, cgbs, dt, kind, sample = run_reference_sample(2, 1, os.cpu_count() or 1)
+                cpu = {"value": gf, "unit": "GFLOP/s", "cores": os.cpu_count() or 1, "kind": kind,
+                       "sample": sample, "gbs": cgbs}
+            except Exception as ex:  # the checker is optional for the measurement itself
+                cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        line = {
+            "metric": "c2c GFLOP/s (5N*log2N), 1d double-batched sweep N=2..512",
+            "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(world),
+            "gbs": gbs, "gbs_frac_of_peak": gbs / world / peak,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * steps, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    for _, _, _, p in plans:
+        p.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

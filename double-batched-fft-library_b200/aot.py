@@ -10,16 +10,34 @@ import subprocess
 from . import capi
 from .build import ARCH_FLAGS, HERE, KERNELS, NVCC, CXX
 
+def smooth_sizes(lo=2, hi=512, primes=(2, 3, 5, 7)):
+    """The reference's benchmark sweep sizes (tools/powers.py -p 4 2 512): 7-smooth numbers."""
+    out = []
+    for n in range(lo, hi + 1):
+        m = n
+        for p in primes:
+            while m % p == 0:
+                m //= p
+        if m == 1:
+            out.append(n)
+    return out
+
+
+def sweep_k(n, fp, nbytes=1 << 30, m=16):
+    """K of the reference benchmark: input tensor of `nbytes` (benchmark/test.hpp:18-30)."""
+    return max(1, nbytes // (m * n * 2 * fp))
+
+
 # FFT descriptors (reference docs/manual/descriptor.rst) of the configurations BASELINE.json names
 BUILTIN_DESCRIPTORS = (
     ["scfo64*16384"]
-    + ["scfo16.%d*%d" % (n, (1 << 30) // (16 * n * 8)) for n in (2, 4, 8, 16, 32, 64, 128, 256, 512)]
-    + ["dcfo16.%d*%d" % (n, (1 << 30) // (16 * n * 16)) for n in (2, 4, 8, 16, 32, 64, 128, 256, 512)]
+    + ["scfo16.%d*%d" % (n, sweep_k(n, 4)) for n in smooth_sizes()]
+    + ["dcfo16.%d*%d" % (n, sweep_k(n, 8)) for n in smooth_sizes()]
 )
 
 
 def compile_bundle(descriptors, out_path, verbose=False):
-    """descriptors -> cubin at out_path; returns the kernel names inside."""
+    """descriptors -> cubin at out_path (nvcc, sm_100a); returns the kernel names inside."""
     cfgs = [capi.parse_descriptor(d) for d in descriptors]
     source, names = capi.generate_kernels(cfgs)
     cu = os.path.splitext(out_path)[0] + ".cu"
@@ -30,17 +48,33 @@ def compile_bundle(descriptors, out_path, verbose=False):
             "-I" + KERNELS, "-cubin", "-o", out_path, cu]
         if verbose:
             print(" ".join(cmd))
-        subprocess.check_call(cmd)
-    return names
+        return names, subprocess.Popen(cmd)
+    return names, None
 
 
-def build_builtin(verbose=False):
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
-    out = os.path.join(HERE, "builtin_kernels.cubin")
-    names = compile_bundle(BUILTIN_DESCRIPTORS, os.path.join(HERE, "build", "builtin_kernels.cubin"), verbose)
-    # publish atomically next to the library
-    tmp = out + ".tmp"
-    with open(os.path.join(HERE, "build", "builtin_kernels.cubin"), "rb") as f, open(tmp, "wb") as g:
-        g.write(f.read())
-    os.replace(tmp, out)
-    return names
+def build_builtin(verbose=False, jobs=8):
+    """Built-in bundles builtin_kernels_<i>.cubin next to the library (compiled in parallel)."""
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    header = os.path.join(KERNELS, "bbfft_kernels.cuh")
+    chunks = [BUILTIN_DESCRIPTORS[i::jobs] for i in range(jobs)]
+    procs = []
+    all_names = []
+    for i, chunk in enumerate(chunks):
+        out = os.path.join(bdir, "builtin_kernels_%d.cubin" % i)
+        if os.path.exists(out) and os.path.getmtime(out) < os.path.getmtime(header):
+            os.remove(out)
+        names, proc = compile_bundle(chunk, out, verbose)
+        all_names += names
+        procs.append((out, proc))
+    for out, proc in procs:
+        if proc is not None and proc.wait() != 0:
+            raise RuntimeError("nvcc failed for " + out)
+    # publish next to the library, dropping stale bundles
+    for f in os.listdir(HERE):
+        if f.startswith("builtin_kernels") and f.endswith(".cubin"):
+            os.remove(os.path.join(HERE, f))
+    for out, _ in procs:
+        with open(out, "rb") as f, open(os.path.join(HERE, os.path.basename(out)), "wb") as g:
+            g.write(f.read())
+    return all_names

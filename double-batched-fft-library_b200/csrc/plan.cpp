@@ -14,6 +14,7 @@
 
 #include "bbfft/cuda/online_compiler.hpp"
 
+#include <dirent.h>
 #include <dlfcn.h>
 
 #include <fstream>
@@ -100,10 +101,10 @@ problem_1d to_problem(configuration const &cfg) {
 // ------------------------------------------------------------------------------------------
 namespace {
 struct builtin_bundle {
-    std::vector<char> image;
+    std::vector<std::vector<char>> images;
     bool tried = false;
     std::mutex mtx;
-    std::map<int, aot_module> per_device;
+    std::map<int, std::vector<aot_module>> per_device;
 };
 builtin_bundle &bundle() {
     static builtin_bundle b;
@@ -119,26 +120,42 @@ shared_handle<module_handle_t> builtin_module(std::string const &kernel_name, in
         char const *off = std::getenv("BBFFT_CUDA_NO_BUILTIN");
         Dl_info info;
         if (!(off && *off == '1') && dladdr(reinterpret_cast<void *>(&builtin_module), &info) && info.dli_fname) {
-            std::string path(info.dli_fname);
-            auto slash = path.find_last_of('/');
-            path = (slash == std::string::npos ? std::string(".") : path.substr(0, slash)) + "/builtin_kernels.cubin";
-            std::ifstream f(path, std::ios::binary);
-            if (f) b.image.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            std::string dir(info.dli_fname);
+            auto slash = dir.find_last_of('/');
+            dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+            if (DIR *d = opendir(dir.c_str())) {
+                while (dirent *e = readdir(d)) {
+                    std::string name(e->d_name);
+                    if (name.rfind("builtin_kernels", 0) != 0 || name.size() < 6 ||
+                        name.substr(name.size() - 6) != ".cubin") {
+                        continue;
+                    }
+                    std::ifstream f(dir + "/" + name, std::ios::binary);
+                    if (f) {
+                        b.images.emplace_back(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+                    }
+                }
+                closedir(d);
+            }
         }
     }
-    if (b.image.empty()) return {};
+    if (b.images.empty()) return {};
     auto it = b.per_device.find(device);
     if (it == b.per_device.end()) {
-        try {
-            auto m = create_aot_module(reinterpret_cast<std::uint8_t const *>(b.image.data()), b.image.size(),
-                                       module_format::native, device);
-            it = b.per_device.emplace(device, std::move(m)).first;
-        } catch (std::exception const &) {
-            b.image.clear(); // unusable on this device (e.g. other architecture): fall back to JIT
-            return {};
+        std::vector<aot_module> mods;
+        for (auto const &img : b.images) {
+            try {
+                mods.push_back(create_aot_module(reinterpret_cast<std::uint8_t const *>(img.data()), img.size(),
+                                                 module_format::native, device));
+            } catch (std::exception const &) {
+                // unusable on this device (e.g. other architecture): those kernels are JIT-compiled
+            }
         }
+        it = b.per_device.emplace(device, std::move(mods)).first;
     }
-    if (it->second.kernel_names.count(kernel_name)) return it->second.mod;
+    for (auto const &m : it->second) {
+        if (m.kernel_names.count(kernel_name)) return m.mod;
+    }
     return {};
 }
 

@@ -1,0 +1,100 @@
+"""CPU tier: the host side of the product (no GPU): the C-ABI library loads and exports every
+symbol include/bbfft_cuda.h declares, descriptors / strides / planner behave like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "bbfft_cuda.h")).read()
+    names = set(re.findall(r"\b(bbfft_cuda_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 18
+    lib = ctypes.CDLL(os.path.join(ROOT, "double-batched-fft-library_b200", "libbbfft_cuda.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+
+
+def test_default_strides(pkg):
+    # reference src/base/configuration.cpp:24-56, docs/manual/data-layout.rst
+    assert pkg.default_strides(1, [4, 10, 3], pkg.C2C, True) == ([1, 4, 40, 0, 0], [1, 4, 40, 0, 0])
+    assert pkg.default_strides(1, [4, 10, 3], pkg.R2C, True) == ([1, 4, 48, 0, 0], [1, 4, 24, 0, 0])
+    assert pkg.default_strides(1, [4, 10, 3], pkg.R2C, False) == ([1, 4, 40, 0, 0], [1, 4, 24, 0, 0])
+    assert pkg.default_strides(1, [4, 10, 3], pkg.C2R, False) == ([1, 4, 24, 0, 0], [1, 4, 40, 0, 0])
+    assert pkg.default_strides(3, [2, 5, 6, 7, 3], pkg.R2C, True) == ([1, 2, 12, 72, 504], [1, 2, 6, 36, 252])
+    assert pkg.default_strides(1, [1, 256, 8], pkg.R2C, True)[0][:3] == [1, 1, 258]
+
+
+@pytest.mark.parametrize("desc,dim,shape,fp,d,t", [
+    ("srfi5", 1, [1, 5, 1], 4, -1, 1),
+    ("dcbi4*5", 1, [1, 4, 5], 8, 1, 0),
+    ("dcbi4.5", 1, [4, 5, 1], 8, 1, 0),
+    ("drbo4.5*6", 1, [4, 5, 6], 8, 1, 2),
+    ("drfo5x6x7", 3, [1, 5, 6, 7, 1], 8, -1, 1),
+    ("srbo4.5x6*7", 2, [4, 5, 6, 7], 4, 1, 2),
+    ("scfo16*32i1,1,20", 1, [1, 16, 32], 4, -1, 0),
+    ("scfo16*32i1,1,20o1,2,32", 1, [1, 16, 32], 4, -1, 0),
+    ("scfi16*32i1,1,20o1,1,20", 1, [1, 16, 32], 4, -1, 0),
+])
+def test_descriptor_round_trip(pkg, desc, dim, shape, fp, d, t):
+    # reference test/parser.cpp:33-126
+    c = pkg.parse_descriptor(desc)
+    assert c.dim == dim and list(c.shape)[: len(shape)] == shape
+    assert (c.fp, c.dir, c.type) == (fp, d, t)
+    assert pkg.to_descriptor(c) == desc
+
+
+@pytest.mark.parametrize("bad", ["", "x", "scf", "scfo", "scfox", "scfo5x", "scfo1.2.3", "scfo2x3x4x5", "scfo5i1,2", "scfo5q"])
+def test_descriptor_malformed(pkg, bad):
+    with pytest.raises(pkg.BbfftError):
+        pkg.parse_descriptor(bad)
+
+
+def test_identifier_is_independent_of_k(pkg):
+    # K is a run-time argument, not part of the cache key (reference examples/cache/main.cpp:50-52)
+    a = pkg.describe(pkg.make_config(1, [16, 64, 1000], 4))
+    b = pkg.describe(pkg.make_config(1, [16, 64, 5000], 4))
+    assert a["identifier"] == b["identifier"]
+    c = pkg.describe(pkg.make_config(1, [16, 64, 1000], 8))
+    assert c["identifier"] != a["identifier"]
+
+
+def test_planner_covers_the_sweep(pkg):
+    aot = __import__("importlib").import_module("double-batched-fft-library_b200.aot")
+    sizes = aot.smooth_sizes()
+    assert len(sizes) == 105 and sizes[:6] == [2, 3, 4, 5, 6, 7] and sizes[-1] == 512
+    for fp in (4, 8):
+        for n in sizes:
+            d = pkg.describe(pkg.make_config(1, [16, n, 64], fp, inplace=False))
+            prod = int(np.prod(d["radix"]))
+            assert prod == n
+            assert d["threads"] <= 1024 and d["smem_bytes"] <= 227 * 1024
+            assert d["grid"] >= 1
+
+
+def test_bad_configurations(pkg):
+    # stride[0] != 1 -> bad_configuration; r2c must be forward (reference src/base/configuration.cpp:107-111)
+    c = pkg.make_config(1, [4, 8, 2], 4, istride=[2, 8, 64], ostride=[1, 4, 32])
+    with pytest.raises(pkg.BadConfiguration):
+        pkg.describe(c)
+    c = pkg.make_config(1, [4, 8, 2], 4, pkg.BACKWARD, pkg.R2C)
+    with pytest.raises(pkg.BadConfiguration):
+        pkg.describe(c)
+
+
+def test_generate_kernels_and_nvrtc_cross_compile(pkg):
+    """generate_fft_kernels emits one stub per distinct kernel; NVRTC builds it for sm_100a
+    without a GPU (the product's JIT path, minus the module load)."""
+    cfgs = [pkg.parse_descriptor(d) for d in ("scfo16.64*100", "scfo16.64*200", "dcfo8x8*4")]
+    src, names = pkg.generate_kernels(cfgs)
+    assert len(names) == len(set(names)) == 3  # same 1d kernel for both K; two passes for the 2d plan
+    for n in names:
+        assert ("extern \"C\" BBK_GLOBAL" in src) and n in src
+    cubin = pkg.compile_to_cubin(src)
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 4096
+    for n in names:
+        assert n.encode() in cubin
