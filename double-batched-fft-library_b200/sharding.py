@@ -19,12 +19,10 @@ def shard_k(K, world, rank, pair_align=False):
 def shard_config(pkg, cfg, world, rank):
     """Per-rank configuration (same kernel, K_local slices) and the element offsets of the slab
     in the input and output tensors."""
-    import copy
     dim = cfg.dim
     K = cfg.shape[dim + 1]
     odd_real = cfg.type != 0 and cfg.shape[1] % 2 == 1
     k0, k1 = shard_k(K, world, rank, pair_align=odd_real)
-    local = copy.copy(cfg)
     shape = list(cfg.shape)
     shape[dim + 1] = k1 - k0
     local = pkg.make_config(dim, shape[: dim + 2], cfg.fp, cfg.dir, cfg.type, istride=list(cfg.istride)[: dim + 2],

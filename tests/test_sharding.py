@@ -46,7 +46,7 @@ def _worker(rank, world, port, q):
     pkg = importlib.import_module("double-batched-fft-library_b200")
     sh = importlib.import_module("double-batched-fft-library_b200.sharding")
     from oracle import oracle
-    M, N, K = 4, 12, 9
+    M, N, K = 4, 12, 600  # large enough that the CTA batch size does not depend on the slab
     rng = np.random.default_rng(3)
     x = (rng.standard_normal((K, N, M)) + 1j * rng.standard_normal((K, N, M))).astype(np.complex128)
     cfg = pkg.make_config(1, [M, N, K], 8, pkg.FORWARD, pkg.C2C, inplace=False)
