@@ -12,6 +12,9 @@
 #include "runtime.hpp"
 
 #include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <cstring>
 #include <sstream>
 #include <string>
@@ -89,9 +92,50 @@ struct bbfft_cuda_plan_s {
     std::shared_ptr<cuda::plan_base> impl;
     std::vector<std::string> kernel_names;
     int device = 0;
-    void *dev_in = nullptr, *dev_out = nullptr;
-    size_t dev_in_bytes = 0, dev_out_bytes = 0;
 };
+
+namespace {
+// Device staging for the host-buffer entry point: one pair of buffers and two copy streams per
+// device, shared by all plans (grown on demand, released at process exit).
+struct staging {
+    std::mutex mtx;
+    void *in = nullptr, *out = nullptr;
+    size_t in_bytes = 0, out_bytes = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    void reserve(size_t need_in, size_t need_out) {
+        if (in_bytes < need_in) {
+            if (in) cudaFree(in);
+            in = nullptr;
+            in_bytes = 0;
+            BBFFT_CUDA_CHECK(cudaMalloc(&in, need_in));
+            in_bytes = need_in;
+        }
+        if (out_bytes < need_out) {
+            if (out) cudaFree(out);
+            out = nullptr;
+            out_bytes = 0;
+            BBFFT_CUDA_CHECK(cudaMalloc(&out, need_out));
+            out_bytes = need_out;
+        }
+    }
+    void ensure_streams() {
+        if (!streams[0]) {
+            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&streams[0], cudaStreamNonBlocking));
+            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&streams[1], cudaStreamNonBlocking));
+            BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        }
+    }
+};
+staging &staging_for(int device) {
+    static std::mutex m;
+    static std::map<int, std::unique_ptr<staging>> all;
+    std::lock_guard<std::mutex> lock(m);
+    auto &p = all[device];
+    if (!p) p = std::make_unique<staging>();
+    return *p;
+}
+} // namespace
 
 extern "C" {
 
@@ -175,31 +219,49 @@ int bbfft_cuda_plan_execute_host(bbfft_cuda_plan_t plan, const void *host_in, si
     return guarded([&] {
         cudaStream_t s = plan->impl->stream();
         const bool inplace = host_in == host_out;
-        size_t need_in = inplace ? std::max(in_bytes, out_bytes) : in_bytes;
-        if (plan->dev_in_bytes < need_in) {
-            if (plan->dev_in) cudaFree(plan->dev_in);
-            BBFFT_CUDA_CHECK(cudaMalloc(&plan->dev_in, need_in));
-            plan->dev_in_bytes = need_in;
+        auto &st = staging_for(plan->device);
+        std::lock_guard<std::mutex> lock(st.mtx);
+        st.reserve(inplace ? std::max(in_bytes, out_bytes) : in_bytes, inplace ? 0 : out_bytes);
+        void *din = st.in;
+        void *dout = inplace ? st.in : st.out;
+        const std::uint64_t K = plan->impl->slices();
+        const std::size_t isl = plan->impl->in_slice_bytes(), osl = plan->impl->out_slice_bytes();
+        // Sliceable plans are pipelined over k slabs on two streams so that the H2D copy of slab
+        // c+1 overlaps the kernel and the D2H copy of slab c (PCIe is full duplex).
+        std::uint64_t chunks = 1;
+        if (K > 1 && isl > 0 && osl > 0 && K * isl <= in_bytes + isl && (in_bytes + out_bytes) > (32u << 20)) {
+            chunks = std::min<std::uint64_t>(8, K / 2);
         }
-        if (!inplace && plan->dev_out_bytes < out_bytes) {
-            if (plan->dev_out) cudaFree(plan->dev_out);
-            BBFFT_CUDA_CHECK(cudaMalloc(&plan->dev_out, out_bytes));
-            plan->dev_out_bytes = out_bytes;
+        if (chunks <= 1) {
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, host_in, in_bytes, cudaMemcpyHostToDevice, s));
+            plan->impl->enqueue(din, dout, s);
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, s));
+            BBFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+            return;
         }
-        void *din = plan->dev_in;
-        void *dout = inplace ? plan->dev_in : plan->dev_out;
-        BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, host_in, in_bytes, cudaMemcpyHostToDevice, s));
-        plan->impl->enqueue(din, dout, s);
-        BBFFT_CUDA_CHECK(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, s));
-        BBFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+        st.ensure_streams();
+        BBFFT_CUDA_CHECK(cudaEventRecord(st.ev, s));
+        std::uint64_t per = ((K + chunks - 1) / chunks + 1) & ~std::uint64_t(1); // even: odd-N real pairs
+        for (std::uint64_t c = 0, k0 = 0; k0 < K; ++c, k0 += per) {
+            std::uint64_t cnt = std::min(per, K - k0);
+            cudaStream_t cs = st.streams[c % 2];
+            if (c < 2) BBFFT_CUDA_CHECK(cudaStreamWaitEvent(cs, st.ev, 0));
+            std::size_t ioff = k0 * isl, ooff = k0 * osl;
+            std::size_t ib = std::min(cnt * isl, in_bytes > ioff ? in_bytes - ioff : 0);
+            std::size_t ob = std::min(cnt * osl, out_bytes > ooff ? out_bytes - ooff : 0);
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(din) + ioff, static_cast<char const *>(host_in) + ioff,
+                                             ib, cudaMemcpyHostToDevice, cs));
+            plan->impl->enqueue_slab(din, dout, k0, cnt, cs);
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(host_out) + ooff, static_cast<char *>(dout) + ooff, ob,
+                                             cudaMemcpyDeviceToHost, cs));
+        }
+        BBFFT_CUDA_CHECK(cudaStreamSynchronize(st.streams[0]));
+        BBFFT_CUDA_CHECK(cudaStreamSynchronize(st.streams[1]));
     });
 }
 
 int bbfft_cuda_plan_destroy(bbfft_cuda_plan_t plan) {
     return guarded([&] {
-        if (!plan) return;
-        if (plan->dev_in) cudaFree(plan->dev_in);
-        if (plan->dev_out) cudaFree(plan->dev_out);
         delete plan;
     });
 }

@@ -381,70 +381,83 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
     using WR = typename C::template WR<S>;
     const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + C::tw_off(S);
 
-    cx<T> v[CNT][R];
-    // ---- gather
-    static_for<0, CNT>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int u = t + C::T * i;
-        if (NSUB % C::T == 0 || u < NSUB) {
-            const int n2 = u % NS1, q = u / NS1;
-            const int base = q * NS + n2;
-            static_for<0, R>([&](auto jj) {
-                constexpr int j = decltype(jj)::value;
-                const int pos = base + NS1 * j;
-                if constexpr (SRC == IO_GLOBAL) {
+    // butterflies + inter-stage twiddles of sub-FFT u held in w[0..R-1]
+    auto compute = [&](cx<T> *w, int u) {
+        reg_fft<T, WR, R, C::DIR>::run(w);
+        if constexpr (!LAST) {
+            const int n2 = u % NS1;
+            static_for<1, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                w[q] = cmul(w[q], ldg_cx(tw + (q - 1) * NS1 + n2));
+            });
+        }
+    };
+    auto scatter = [&](cx<T> *w, int u) {
+        if constexpr (DST == IO_GLOBAL) {
+            static_assert(LAST, "only the last stage stores to global memory");
+            const int k0 = bin_of_sub<C>(u);
+            if (ok) {
+                static_for<0, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    const int bin = k0 + (C::N / R) * q;
+                    C::st(a.out, m + u64(bin) * C::os1(a) + k * C::os2(a), w[q]);
+                });
+            }
+        } else {
+            const int n2 = u % NS1, qi = u / NS1;
+            const int base = qi * NS + n2;
+            static_for<0, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                sm[G::soff(b, base + NS1 * q)] = w[q];
+            });
+        }
+    };
+
+    if constexpr (SRC == IO_GLOBAL) {
+        // first stage: issue every global load of the thread before any arithmetic so that all
+        // CNT*R requests are in flight together
+        cx<T> v[CNT][R];
+        static_for<0, CNT>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const int u = t + C::T * i;
+            if (NSUB % C::T == 0 || u < NSUB) {
+                static_for<0, R>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    const int pos = u + NS1 * j; // stage 0: q = 0, n2 = u
                     if (ok) {
                         v[i][j] = C::ld(a.in, m + u64(pos) * C::is1(a) + k * C::is2(a));
                     } else {
                         v[i][j] = cx<T>{T(0), T(0)};
                     }
-                } else {
-                    v[i][j] = sm[G::soff(b, pos)];
-                }
-            });
-        }
-    });
-    // ---- butterflies + inter-stage twiddles
-    static_for<0, CNT>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int u = t + C::T * i;
-        if (NSUB % C::T == 0 || u < NSUB) {
-            reg_fft<T, WR, R, C::DIR>::run(v[i]);
-            if constexpr (!LAST) {
-                const int n2 = u % NS1;
-                static_for<1, R>([&](auto qq) {
-                    constexpr int q = decltype(qq)::value;
-                    cx<T> w = ldg_cx(tw + (q - 1) * NS1 + n2);
-                    v[i][q] = cmul(v[i][q], w);
                 });
             }
-        }
-    });
-    // ---- scatter
-    static_for<0, CNT>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int u = t + C::T * i;
-        if (NSUB % C::T == 0 || u < NSUB) {
-            if constexpr (DST == IO_GLOBAL) {
-                static_assert(LAST, "only the last stage stores to global memory");
-                const int k0 = bin_of_sub<C>(u);
-                if (ok) {
-                    static_for<0, R>([&](auto qq) {
-                        constexpr int q = decltype(qq)::value;
-                        const int bin = k0 + (C::N / R) * q;
-                        C::st(a.out, m + u64(bin) * C::os1(a) + k * C::os2(a), v[i][q]);
-                    });
-                }
-            } else {
-                const int n2 = u % NS1, qi = u / NS1;
-                const int base = qi * NS + n2;
-                static_for<0, R>([&](auto qq) {
-                    constexpr int q = decltype(qq)::value;
-                    sm[G::soff(b, base + NS1 * q)] = v[i][q];
-                });
+        });
+        static_for<0, CNT>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const int u = t + C::T * i;
+            if (NSUB % C::T == 0 || u < NSUB) {
+                compute(v[i], u);
+                scatter(v[i], u);
             }
-        }
-    });
+        });
+    } else {
+        // shared-memory stages: one sub-FFT at a time keeps only R elements live
+        static_for<0, CNT>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const int u = t + C::T * i;
+            if (NSUB % C::T == 0 || u < NSUB) {
+                cx<T> w[R];
+                const int n2 = u % NS1, q = u / NS1;
+                const int base = q * NS + n2;
+                static_for<0, R>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    w[j] = sm[G::soff(b, base + NS1 * j)];
+                });
+                compute(w, u);
+                scatter(w, u);
+            }
+        });
+    }
 }
 
 #ifdef BBFFT_EMU

@@ -171,6 +171,11 @@ fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::s
     : api_(std::move(a)) {
     auto prob = to_problem(cfg);
     K_ = prob.K;
+    {
+        std::size_t real_bytes = static_cast<std::size_t>(cfg.fp);
+        in_slice_bytes_ = std::size_t(prob.is2) * (cfg.type == transform_type::r2c ? 1 : 2) * real_bytes;
+        out_slice_bytes_ = std::size_t(prob.os2) * (cfg.type == transform_type::c2r ? 1 : 2) * real_bytes;
+    }
     kp_ = plan_kernel_1d(prob, api_.props(), tune.empty() ? env_tune() : tune);
     jit_cache_key key{kp_.identifier, api_.device_id()};
     if (cache) module_ = cache->get(key);
@@ -186,20 +191,26 @@ fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::s
 fft1d_plan::~fft1d_plan() { api_.release_buffer(twiddle_); }
 
 void fft1d_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
+    enqueue_slab(in, out, 0, K_, stream);
+}
+
+void fft1d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
+                              cudaStream_t stream) {
     if (in == out && kp_.inplace_unsupported) {
         throw bad_configuration("The plan does not support in-place transform on the current device.");
     }
+    if (k0 + count > K_) throw bad_configuration("slab exceeds the planned batch");
     kernel_args a;
-    a.in = in;
-    a.out = out;
+    a.in = static_cast<char const *>(in) + k0 * in_slice_bytes_;
+    a.out = static_cast<char *>(out) + k0 * out_slice_bytes_;
     a.tw = twiddle_;
-    a.K = K_;
+    a.K = count;
     a.M = kp_.p.M;
     a.is1 = kp_.p.is1;
     a.is2 = kp_.p.is2;
     a.os1 = kp_.p.os1;
     a.os2 = kp_.p.os2;
-    api_.launch_kernel(kernel_, kp_.p.grid(K_), kp_.p.threads, kp_.p.smem_bytes, a, stream);
+    api_.launch_kernel(kernel_, kp_.p.grid(count), kp_.p.threads, kp_.p.smem_bytes, a, stream);
 }
 
 auto plan_base::execute(void const *in, void *out, std::vector<event> const &dep_events) -> event {

@@ -26,6 +26,15 @@ class plan_base : public detail::plan_impl<event> {
     virtual void enqueue(void const *in, void *out, cudaStream_t stream) = 0;
     virtual cudaStream_t stream() const = 0;
     virtual unsigned launches_per_execute() const = 0;
+    // Slab interface for host-side pipelining / sharding: number of independent k slices, the
+    // byte extent of one slice in the input/output tensor (0 = not sliceable), and a launch over
+    // slices [k0, k0 + count) given the base pointers of the whole tensors.
+    virtual std::uint64_t slices() const { return 0; }
+    virtual std::size_t in_slice_bytes() const { return 0; }
+    virtual std::size_t out_slice_bytes() const { return 0; }
+    virtual void enqueue_slab(void const *, void *, std::uint64_t, std::uint64_t, cudaStream_t) {
+        throw bad_configuration("plan cannot be sliced");
+    }
     auto execute(void const *in, void *out, std::vector<event> const &dep_events) -> event override;
 };
 
@@ -40,11 +49,17 @@ class fft1d_plan : public plan_base {
     cudaStream_t stream() const override { return api_.stream(); }
     unsigned launches_per_execute() const override { return 1; }
     kernel_plan const &kernel() const { return kp_; }
+    std::uint64_t slices() const override { return K_; }
+    std::size_t in_slice_bytes() const override { return in_slice_bytes_; }
+    std::size_t out_slice_bytes() const override { return out_slice_bytes_; }
+    void enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
+                      cudaStream_t stream) override;
 
   private:
     api api_;
     kernel_plan kp_;
     std::uint64_t K_ = 0;
+    std::size_t in_slice_bytes_ = 0, out_slice_bytes_ = 0;
     shared_handle<module_handle_t> module_;
     cudaKernel_t kernel_ = nullptr;
     void *twiddle_ = nullptr;

@@ -494,6 +494,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         throw std::runtime_error("bbfft-cuda planner: shared memory demand too large");
     }
     p.min_blocks = 1;
+    if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
 
     // real in-place transforms need one CTA to own every m of a k slice, like the reference
     // (src/base/generator/small_batch_fft.cpp:38, factor2_slm_fft.cpp:63)
@@ -516,7 +517,7 @@ std::string make_identifier(kernel_params const &p) {
     os << "bbfft_" << mode_names[p.mode] << (p.dir < 0 ? "_m1" : "_p1") << "_f" << (p.fp * 8)
        << "_M" << p.M << "_N" << p.nreal << "_r";
     for (int s = 0; s < p.L; ++s) os << (s ? "x" : "") << p.radix[s];
-    os << "_T" << p.T << "_ML" << p.ML << "_BH" << p.BH << "_kl" << int(p.klanes) << "_ld"
+    os << "_T" << p.T << "_ML" << p.ML << "_BH" << p.BH << "_mb" << p.min_blocks << "_kl" << int(p.klanes) << "_ld"
        << int(p.load_staged) << "_st" << int(p.store_staged) << "_pk" << p.PADK << "_row" << p.ROW
        << "_is" << p.is1 << "_" << p.is2 << "_os" << p.os1 << "_" << p.os2;
     if (!p.cb_load.empty()) os << "_" << p.cb_load;

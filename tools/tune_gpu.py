@@ -1,0 +1,152 @@
+"""Auto-tuner for the 1d c2c kernels (M=16 sweep family): times planner overrides on the GPU and
+writes the best per (fp, N) as JSON "wisdom".  NVRTC compiles run on a thread pool.
+Usage: python tools/tune_gpu.py --fp 4,8 --sizes 343,512 --out gpurun_out/wisdom.json [--minN 33]
+"""
+import argparse
+import importlib
+import itertools
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("double-batched-fft-library_b200")
+aot = importlib.import_module("double-batched-fft-library_b200.aot")
+
+
+def factorizations(n, max_r, max_l):
+    out = []
+
+    def rec(rem, lo, cur):
+        if rem == 1:
+            if cur:
+                out.append(list(cur))
+            return
+        if len(cur) >= max_l:
+            return
+        for r in range(lo, min(rem, max_r) + 1):
+            if rem % r == 0:
+                cur.append(r)
+                rec(rem // r, r, cur)
+                cur.pop()
+    rec(n, 2, [])
+    return out
+
+
+def candidates(n, fp, M):
+    full = 128 // (2 * fp)
+    cands = [""]
+    single_max = 64 if fp == 4 else 32
+    facs = []
+    if n <= single_max:
+        facs.append([n])
+    for L, max_r, top in ((2, 32 if fp == 4 else 25, 3), (3, 16, 3), (4, 8, 1 if n > 300 else 0)):
+        f = [x for x in factorizations(n, max_r, L) if len(x) == L]
+        f.sort(key=lambda x: (max(x), sum(x)))
+        facs += f[:top]
+    seen = set()
+    for f in facs:
+        if len(f) == 1:
+            for bh in (4, 8, 16):
+                cands.append("R=%d,T=1,BH=%d" % (f[0], bh))
+            continue
+        ts = set()
+        for c in (1, 2):
+            t = -(-(n // max(f)) // c)
+            regs = max(-(-(n // r) // t) * r for r in f)
+            if regs <= (32 if fp == 4 else 20):
+                ts.add(t)
+        for t in ts:
+            for ml in {full, max(2, full // 2)}:
+                if ml * t > 1024:
+                    continue
+                for mb in (1, 2, 3):
+                    bhs = {max(1, 256 // (ml * t)), max(1, 128 // (ml * t))}
+                    for bh in bhs:
+                        thr = ml * t * bh
+                        if thr > 1024 or thr * mb > 2048:
+                            continue
+                        if ml * bh * n * 2 * fp * mb > 220 * 1024:
+                            continue
+                        s = "R=%s,T=%d,ML=%d,BH=%d,MB=%d" % ("x".join(map(str, f)), t, ml, bh, mb)
+                        if s not in seen:
+                            seen.add(s)
+                            cands.append(s)
+    return cands
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--fp", default="4,8")
+    ap.add_argument("--sizes", default="")
+    ap.add_argument("--minN", type=int, default=2)
+    ap.add_argument("--M", type=int, default=16)
+    ap.add_argument("--bytes", type=int, default=1 << 30)
+    ap.add_argument("--out", default="gpurun_out/wisdom.json")
+    ap.add_argument("--threads", type=int, default=min(32, os.cpu_count() or 8))
+    ap.add_argument("--budget", type=float, default=1e9, help="stop after this many seconds")
+    args = ap.parse_args()
+    sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [n for n in aot.smooth_sizes() if n >= args.minN]
+    stream = torch.cuda.current_stream().cuda_stream
+    M = args.M
+    results = {}
+    t_start = time.time()
+    pool = ThreadPoolExecutor(args.threads)
+    xbuf = {4: torch.rand(args.bytes // 4, dtype=torch.float32, device="cuda"),
+            8: torch.rand(args.bytes // 8, dtype=torch.float64, device="cuda")}
+    ybuf = {4: torch.empty_like(xbuf[4]), 8: torch.empty_like(xbuf[8])}
+    for fp in [int(f) for f in args.fp.split(",")]:
+        for n in sizes:
+            if time.time() - t_start > args.budget:
+                break
+            K = max(1, args.bytes // (M * n * 2 * fp))
+            cfg = pkg.make_config(1, [M, n, K], fp, pkg.FORWARD, pkg.C2C, inplace=False)
+            cands = candidates(n, fp, M)
+
+            def mk(tune):
+                try:
+                    return tune, pkg.Plan(cfg, stream=stream, tune=tune)
+                except Exception as ex:
+                    return tune, None
+            plans = list(pool.map(mk, cands))
+            x, y = xbuf[fp], ybuf[fp]
+            timings = []
+            for tune, plan in plans:
+                if plan is None:
+                    continue
+                for _ in range(2):
+                    plan.execute(x, y)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                best = 1e9
+                for _ in range(3):
+                    e0.record()
+                    plan.execute(x, y)
+                    e1.record()
+                    e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                timings.append((best, tune, plan.kernel_names[0]))
+                plan.close()
+            timings.sort()
+            nbytes = 2.0 * M * n * K * 2 * fp
+            default = [t for t in timings if t[1] == ""]
+            best = timings[0]
+            results["%d,%d" % (fp, n)] = {"best": best[1], "gbs": nbytes / best[0] * 1e-6,
+                                          "default_gbs": nbytes / default[0][0] * 1e-6 if default else None,
+                                          "top": [(t[1], round(nbytes / t[0] * 1e-6)) for t in timings[:5]],
+                                          "n_cands": len(timings)}
+            print(fp, n, "best %s %.0f GB/s (default %.0f) of %d cands; top: %s" % (
+                best[1], nbytes / best[0] * 1e-6, nbytes / default[0][0] * 1e-6 if default else -1, len(timings),
+                results["%d,%d" % (fp, n)]["top"][1:4]), flush=True)
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
