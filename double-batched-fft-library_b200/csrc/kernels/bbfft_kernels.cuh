@@ -365,7 +365,64 @@ template <class C> struct batch_index {
 };
 
 // One Stockham pass.  SRC/DST select where the elements come from / go to.
-enum : int { IO_GLOBAL = 0, IO_SMEM = 1 };
+enum : int {
+    IO_GLOBAL = 0,  // complex tensor in global memory
+    IO_SMEM = 1,    // the CTA's shared-memory rows
+    IO_G_RPAIR = 2, // real tensor, element j = (x[2j], x[2j+1])            (even-N real transforms)
+    IO_G_2ROWS = 3  // real tensor, element n = (x_{2k}[n], x_{2k+1}[n])    (odd-N real transforms)
+};
+
+// first-stage element load from global memory; `k` is the k slice (IO_G_2ROWS: the slice pair)
+template <class C, int SRC>
+BBK_DEV cx<typename C::real_t> load_elem(args const &a, u64 m, u64 k, int pos, bool ok) {
+    using T = typename C::real_t;
+    cx<T> r{T(0), T(0)};
+    if constexpr (SRC == IO_GLOBAL) {
+        if (ok) r = C::ld(a.in, m + u64(pos) * C::is1(a) + k * C::is2(a));
+    } else if constexpr (SRC == IO_G_RPAIR) {
+        if (ok) {
+            if constexpr (C::PAIR_LOAD) {
+                // M == 1, unit stride: the pair is one aligned complex word
+                r = reinterpret_cast<const cx<T> *>(a.in)[(u64(2 * pos) + k * C::is2(a)) / 2];
+            } else {
+                const u64 o = m + u64(2 * pos) * C::is1(a) + k * C::is2(a);
+                r.x = C::ldr(a.in, o);
+                r.y = C::ldr(a.in, o + C::is1(a));
+            }
+        }
+    } else if constexpr (SRC == IO_G_2ROWS) {
+        if (ok) {
+            const u64 o = m + u64(pos) * C::is1(a) + (2 * k) * C::is2(a);
+            r.x = C::ldr(a.in, o);
+            // an unpaired last row is transformed together with zeros
+            // (reference: src/base/generator/snippet.cpp:72-85)
+            r.y = (2 * k + 1 < a.K) ? C::ldr(a.in, o + C::is2(a)) : T(0);
+        }
+    }
+    return r;
+}
+
+// last-stage element store to global memory (`bin` = output index)
+template <class C, int DST>
+BBK_DEV void store_elem(args const &a, u64 m, u64 k, int bin, cx<typename C::real_t> v, bool ok) {
+    if (!ok) return;
+    using T = typename C::real_t;
+    if constexpr (DST == IO_GLOBAL) {
+        C::st(a.out, m + u64(bin) * C::os1(a) + k * C::os2(a), v);
+    } else if constexpr (DST == IO_G_RPAIR) {
+        if constexpr (C::PAIR_STORE) {
+            reinterpret_cast<cx<T> *>(a.out)[(u64(2 * bin) + k * C::os2(a)) / 2] = v;
+        } else {
+            const u64 o = m + u64(2 * bin) * C::os1(a) + k * C::os2(a);
+            C::str(a.out, o, v.x);
+            C::str(a.out, o + C::os1(a), v.y);
+        }
+    } else if constexpr (DST == IO_G_2ROWS) {
+        const u64 o = m + u64(bin) * C::os1(a) + (2 * k) * C::os2(a);
+        C::str(a.out, o, v.x);
+        if (2 * k + 1 < a.K) C::str(a.out, o + C::os2(a), v.y);
+    }
+}
 
 template <class C, int S, int SRC, int DST>
 BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
@@ -393,16 +450,13 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
         }
     };
     auto scatter = [&](cx<T> *w, int u) {
-        if constexpr (DST == IO_GLOBAL) {
+        if constexpr (DST != IO_SMEM) {
             static_assert(LAST, "only the last stage stores to global memory");
             const int k0 = bin_of_sub<C>(u);
-            if (ok) {
-                static_for<0, R>([&](auto qq) {
-                    constexpr int q = decltype(qq)::value;
-                    const int bin = k0 + (C::N / R) * q;
-                    C::st(a.out, m + u64(bin) * C::os1(a) + k * C::os2(a), w[q]);
-                });
-            }
+            static_for<0, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                store_elem<C, DST>(a, m, k, k0 + (C::N / R) * q, w[q], ok);
+            });
         } else {
             const int n2 = u % NS1, qi = u / NS1;
             const int base = qi * NS + n2;
@@ -413,7 +467,7 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
         }
     };
 
-    if constexpr (SRC == IO_GLOBAL) {
+    if constexpr (SRC != IO_SMEM) {
         // first stage: issue every global load of the thread before any arithmetic so that all
         // CNT*R requests are in flight together
         cx<T> v[CNT][R];
@@ -423,12 +477,7 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
             if (NSUB % C::T == 0 || u < NSUB) {
                 static_for<0, R>([&](auto jj) {
                     constexpr int j = decltype(jj)::value;
-                    const int pos = u + NS1 * j; // stage 0: q = 0, n2 = u
-                    if (ok) {
-                        v[i][j] = C::ld(a.in, m + u64(pos) * C::is1(a) + k * C::is2(a));
-                    } else {
-                        v[i][j] = cx<T>{T(0), T(0)};
-                    }
+                    v[i][j] = load_elem<C, SRC>(a, m, k, u + NS1 * j, ok); // stage 0: q = 0, n2 = u
                 });
             }
         });
@@ -504,7 +553,8 @@ BBK_DEV void coop_copy(E *sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, i
             const int b = C::KLANES ? kb : ml + C::ML * kb;
             int pos = n;
             if constexpr (REVERSE) {
-                pos = pos_of_bin<C>(n);
+                // the spectrum of an even-N real transform has one extra bin kept in slot N
+                pos = (NROW > C::N && n == C::N) ? n : pos_of_bin<C>(n);
             }
             const u64 g = m + u64(n) * s1 + k * s2;
             if constexpr (TO_SMEM) {
@@ -557,6 +607,155 @@ template <class C> BBK_DEV void fft1d(args const &a) {
                 sm, m0, k0, C::M, a.K, C::os1(a), C::os2(a), tid, [&](u64) { return cx<T>{}; },
                 [&](u64 g, cx<T> v) { C::st(a.out, g, v); });
         }
+    } else if constexpr (C::MODE == R2C_HALF) {
+        // z[j] = x[2j] + i x[2j+1]; Y = FFT_h(z); X[i] = a + b, X[h-i] = conj(a - b) with
+        // a = (conj(Y[h-i]) + Y[i])/2, b = (conj(Y[h-i]) - Y[i])/2 * (i w_N^i)
+        // (reference: src/base/generator/sbfft_gen.cpp:180-200, f2fft_gen.cpp:253-271)
+        constexpr int H = C::N;
+        if constexpr (C::LOAD_STAGED) {
+            // M == 1: a real row is H aligned complex words
+            coop_copy<C, cx<T>, H, true, false>(
+                sm, m0, k0, C::M, a.K, 1, C::is2(a) / 2, tid,
+                [&](u64 g) { return reinterpret_cast<const cx<T> *>(a.in)[g]; }, [&](u64, cx<T>) {});
+            BBK_SYNC();
+            run_stages<C, 0, IO_SMEM, IO_SMEM>(a, sm, t, b, m, k, ok);
+        } else {
+            run_stages<C, 0, IO_G_RPAIR, IO_SMEM>(a, sm, t, b, m, k, ok);
+        }
+        BBK_SYNC();
+        const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+        constexpr int PAIRS = H / 2 + 1;
+        constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        static_for<0, PCNT>([&](auto cc) {
+            const int i = t + C::T * decltype(cc)::value;
+            if (i < PAIRS) {
+                const int p1 = G::soff(b, pos_of_bin<C>(i));
+                const int p2 = G::soff(b, pos_of_bin<C>((H - i) % H));
+                const cx<T> y1 = sm[p1];
+                const cx<T> y2 = conj(sm[p2]);
+                const cx<T> w = ldg_cx(twr + i);
+                const cx<T> iw = cx<T>{-w.y, w.x};
+                const cx<T> aa = cx<T>{(y2.x + y1.x) * T(0.5), (y2.y + y1.y) * T(0.5)};
+                const cx<T> bb = cmul(cx<T>{(y2.x - y1.x) * T(0.5), (y2.y - y1.y) * T(0.5)}, iw);
+                const cx<T> xi = aa + bb;
+                const cx<T> xh = conj(aa - bb);
+                if constexpr (C::STORE_STAGED) {
+                    // in place: X[i] and X[h-i] take the slots of Y[i] and Y[h-i]; X[h] the extra slot
+                    sm[p1] = xi;
+                    if (i == 0) {
+                        sm[G::soff(b, H)] = xh;
+                    } else if (2 * i != H) {
+                        sm[p2] = xh;
+                    }
+                } else if (ok) {
+                    C::st(a.out, m + u64(i) * C::os1(a) + k * C::os2(a), xi);
+                    if (2 * i != H) C::st(a.out, m + u64(H - i) * C::os1(a) + k * C::os2(a), xh);
+                }
+            }
+        });
+        if constexpr (C::STORE_STAGED) {
+            BBK_SYNC();
+            coop_copy<C, cx<T>, H + 1, false, true>(
+                sm, m0, k0, C::M, a.K, C::os1(a), C::os2(a), tid, [&](u64) { return cx<T>{}; },
+                [&](u64 g, cx<T> v) { C::st(a.out, g, v); });
+        }
+    } else if constexpr (C::MODE == C2R_HALF) {
+        // z[i] = a + b, z[h-i] = conj(a - b) with x1 = X[i] (imag(X[0]) ignored), x2 = conj(X[h-i]),
+        // a = x1 + x2, b = (x1 - x2) * (i w_N^i); x[2j], x[2j+1] = Re, Im of IFFT_h(z)[j]
+        // (reference: src/base/generator/sbfft_gen.cpp:221-247, f2fft_gen.cpp:349-409)
+        constexpr int H = C::N;
+        if constexpr (C::LOAD_STAGED) {
+            coop_copy<C, cx<T>, H + 1, true, false>(
+                sm, m0, k0, C::M, a.K, C::is1(a), C::is2(a), tid,
+                [&](u64 g) { return C::ld(a.in, g); }, [&](u64, cx<T>) {});
+            BBK_SYNC();
+        }
+        const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+        constexpr int PAIRS = H / 2 + 1;
+        constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        static_for<0, PCNT>([&](auto cc) {
+            const int i = t + C::T * decltype(cc)::value;
+            if (i < PAIRS) {
+                cx<T> x1{T(0), T(0)}, x2{T(0), T(0)};
+                if constexpr (C::LOAD_STAGED) {
+                    x1 = sm[G::soff(b, i)];
+                    x2 = sm[G::soff(b, H - i)];
+                } else if (ok) {
+                    x1 = C::ld(a.in, m + u64(i) * C::is1(a) + k * C::is2(a));
+                    x2 = C::ld(a.in, m + u64(H - i) * C::is1(a) + k * C::is2(a));
+                }
+                if (i == 0) x1.y = T(0);
+                x2 = conj(x2);
+                const cx<T> w = ldg_cx(twr + i);
+                const cx<T> iw = cx<T>{-w.y, w.x};
+                const cx<T> aa = x1 + x2;
+                const cx<T> bb = cmul(x1 - x2, iw);
+                if constexpr (C::LOAD_STAGED) {
+                    // every pair must be read before slot i / h-i is overwritten by another
+                    // thread's pair only if pairs shared slots -- they do not (pair i owns {i, h-i})
+                }
+                sm[G::soff(b, i)] = aa + bb;
+                if (i != 0 && 2 * i != H) sm[G::soff(b, H - i)] = conj(aa - bb);
+            }
+        });
+        BBK_SYNC();
+        if constexpr (C::STORE_STAGED) {
+            run_stages<C, 0, IO_SMEM, IO_SMEM>(a, sm, t, b, m, k, ok);
+            BBK_SYNC();
+            // M == 1: a real row is H aligned complex words
+            coop_copy<C, cx<T>, H, false, true>(
+                sm, m0, k0, C::M, a.K, 1, C::os2(a) / 2, tid, [&](u64) { return cx<T>{}; },
+                [&](u64 g, cx<T> v) { reinterpret_cast<cx<T> *>(a.out)[g] = v; });
+        } else {
+            run_stages<C, 0, IO_SMEM, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
+        }
+    } else if constexpr (C::MODE == R2C_DOUBLE) {
+        // rows 2k and 2k+1 are the real and imaginary part of one complex FFT:
+        // A[i] = (conj(Y[N-i]) + Y[i])/2, B[i] = i (conj(Y[N-i]) - Y[i])/2, i <= N/2
+        // (reference: src/base/generator/sbfft_gen.cpp:274-291, f2fft_gen.cpp:314-330)
+        const bool okp = (m < C::M) && (2 * k < a.K);
+        run_stages<C, 0, IO_G_2ROWS, IO_SMEM>(a, sm, t, b, m, k, okp);
+        BBK_SYNC();
+        constexpr int PAIRS = C::N / 2 + 1;
+        constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        static_for<0, PCNT>([&](auto cc) {
+            const int i = t + C::T * decltype(cc)::value;
+            if (i < PAIRS && okp) {
+                const cx<T> y1 = sm[G::soff(b, pos_of_bin<C>(i))];
+                const cx<T> y2 = conj(sm[G::soff(b, pos_of_bin<C>((C::N - i) % C::N))]);
+                const cx<T> av = cx<T>{(y2.x + y1.x) * T(0.5), (y2.y + y1.y) * T(0.5)};
+                const cx<T> d = cx<T>{(y2.x - y1.x) * T(0.5), (y2.y - y1.y) * T(0.5)};
+                const cx<T> bv = cx<T>{-d.y, d.x}; // i * d
+                const u64 o = m + u64(i) * C::os1(a) + (2 * k) * C::os2(a);
+                C::st(a.out, o, av);
+                if (2 * k + 1 < a.K) C::st(a.out, o + C::os2(a), bv);
+            }
+        });
+    } else if constexpr (C::MODE == C2R_DOUBLE) {
+        // Y[i] = A[i] + i B[i], Y[N-i] = conj(A[i]) + i conj(B[i]); rows 2k, 2k+1 = Re, Im of IFFT_N(Y)
+        // (reference: src/base/generator/sbfft_gen.cpp:318-351, f2fft_gen.cpp:443-502)
+        const bool okp = (m < C::M) && (2 * k < a.K);
+        constexpr int PAIRS = C::N / 2 + 1;
+        constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        static_for<0, PCNT>([&](auto cc) {
+            const int i = t + C::T * decltype(cc)::value;
+            if (i < PAIRS) {
+                cx<T> av{T(0), T(0)}, bv{T(0), T(0)};
+                if (okp) {
+                    const u64 o = m + u64(i) * C::is1(a) + (2 * k) * C::is2(a);
+                    av = C::ld(a.in, o);
+                    if (2 * k + 1 < a.K) bv = C::ld(a.in, o + C::is2(a));
+                }
+                if (i == 0) {
+                    av.y = T(0);
+                    bv.y = T(0);
+                }
+                sm[G::soff(b, i)] = cx<T>{av.x - bv.y, av.y + bv.x};
+                if (i != 0) sm[G::soff(b, C::N - i)] = cx<T>{av.x + bv.y, bv.x - av.y};
+            }
+        });
+        BBK_SYNC();
+        run_stages<C, 0, IO_SMEM, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
     }
 }
 

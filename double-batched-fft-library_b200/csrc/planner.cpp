@@ -470,11 +470,19 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         p.store_staged = !rows_ok && prob.M * elem_bytes < 64;
     }
     if (p.mode != k_c2c) {
-        // real transforms do their own pre/post passes (kernel decides), staging flags select
-        // the cooperative row copies
-        if (!(prob.M == 1)) {
-            p.load_staged = false;
-            p.store_staged = false;
+        // Real transforms: the spectrum side is always touched pair-wise (i, N-i) by consecutive
+        // threads, which is coalesced; only the real side of an M == 1 tensor needs help.
+        const bool no_cb = prob.cb_load.empty() && prob.cb_store.empty();
+        p.pair_load = p.mode == k_r2c_half && prob.M == 1 && prob.is1 == 1 && prob.is2 % 2 == 0 && no_cb;
+        p.pair_store = p.mode == k_c2r_half && prob.M == 1 && prob.os1 == 1 && prob.os2 % 2 == 0 && no_cb;
+        p.load_staged = false;
+        p.store_staged = false;
+        if (p.mode == k_r2c_half) {
+            p.load_staged = p.klanes && p.pair_load;
+            p.store_staged = p.klanes;
+        } else if (p.mode == k_c2r_half) {
+            p.load_staged = p.klanes;
+            p.store_staged = prob.M == 1 && p.pair_store;
         }
     }
     // user callbacks see every element exactly once in either path, so staging stays legal.
@@ -520,6 +528,7 @@ std::string make_identifier(kernel_params const &p) {
     os << "_T" << p.T << "_ML" << p.ML << "_BH" << p.BH << "_mb" << p.min_blocks << "_kl" << int(p.klanes) << "_ld"
        << int(p.load_staged) << "_st" << int(p.store_staged) << "_pk" << p.PADK << "_row" << p.ROW
        << "_is" << p.is1 << "_" << p.is2 << "_os" << p.os1 << "_" << p.os2;
+    if (p.mode != k_c2c) os << "_pl" << int(p.pair_load) << "_ps" << int(p.pair_store);
     if (!p.cb_load.empty()) os << "_" << p.cb_load;
     if (!p.cb_store.empty()) os << "_" << p.cb_store;
     std::string s = os.str();
@@ -681,7 +690,9 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
        << ", BH = " << p.BH << ";\n";
     os << "    static constexpr bool KLANES = " << (p.klanes ? "true" : "false")
        << ", LOAD_STAGED = " << (p.load_staged ? "true" : "false")
-       << ", STORE_STAGED = " << (p.store_staged ? "true" : "false") << ";\n";
+       << ", STORE_STAGED = " << (p.store_staged ? "true" : "false")
+       << ", PAIR_LOAD = " << (p.pair_load ? "true" : "false")
+       << ", PAIR_STORE = " << (p.pair_store ? "true" : "false") << ";\n";
     os << "    static constexpr bbk::u64 M = " << p.M << "ull;\n";
     os << "    static constexpr int LL = " << p.LL << ", PADK = " << p.PADK << ", ROW = " << p.ROW
        << ", TW_REAL = " << tw_total << ";\n";

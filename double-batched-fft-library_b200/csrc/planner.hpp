@@ -44,6 +44,7 @@ struct kernel_params {
     int radix[4] = {1, 1, 1, 1};
     int T = 1, ML = 1, BH = 1;
     bool klanes = false, load_staged = false, store_staged = false;
+    bool pair_load = false, pair_store = false; // real side is read/written as aligned complex words
     std::uint64_t M = 1;
     std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1;
     int LL = 1, PADK = 0, ROW = 1;

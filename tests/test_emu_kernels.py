@@ -52,3 +52,52 @@ def test_c2c_emulated_nonpacked_strides(pkg, oracle):
     s = [1, M + 1, (M + 1) * (N + 1)]
     assert _run_c2c(pkg, oracle, M, N, K, 4, -1, istride=s, ostride=s) < TOL[4] * 0.1
     assert _run_c2c(pkg, oracle, M, N, K, 8, 1, istride=s, ostride=[1, M, M * N]) < TOL[8] * 0.1
+
+
+def _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=False):
+    from common import addressed_mask, real_problem
+    rng = np.random.default_rng(ttype * 7919 + M * 131 + N * 17 + K)
+    d = -1 if ttype == 1 else 1
+    ist, ost, x, odt, nout = real_problem(rng, pkg, ttype, M, N, K, fp, inplace, pollute=pollute)
+    cfg = pkg.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace)
+    ocfg = oracle.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace)
+    if inplace:
+        nbytes = max(x.nbytes, nout * np.dtype(odt).itemsize)
+        raw = np.zeros(nbytes, np.uint8)
+        raw[: x.nbytes] = x.view(np.uint8)
+        ref = raw.copy()
+        oracle.dft(ocfg, ref)
+        emu.run(cfg, raw, None)
+        got, want = raw.view(odt)[:nout], ref.view(odt)[:nout]
+    else:
+        want = np.zeros(nout, odt)
+        oracle.dft(ocfg, x, want)
+        got = np.zeros(nout, odt)
+        emu.run(cfg, x, got)
+    mask = addressed_mask(M, N // 2 + 1 if ttype == 1 else N, K, ost, nout)
+    if not inplace:
+        assert np.all(got[~mask] == 0), "kernel wrote outside the addressed elements"
+    return rel_l2(got[mask], want[mask])
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("ttype", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(1, 256, 5), (1, 8, 40), (1, 30, 7), (16, 30, 3), (16, 64, 3), (4, 128, 2), (3, 10, 5),
+                                   (1, 15, 7), (2, 15, 5), (16, 27, 3), (5, 11, 4), (1, 105, 3), (1, 2, 3), (16, 2, 3),
+                                   (1, 512, 2), (16, 500, 1), (1, 3, 1)])
+def test_real_emulated_kernel_vs_oracle(pkg, oracle, fp, ttype, M, N, K):
+    """r2c / c2r, even N (half-length trick) and odd N (two-for-one, incl. odd K), in- and out-of-place."""
+    for inplace in (False, True):
+        d = pkg.describe(pkg.make_config(1, [M, N, K], fp, -1 if ttype == 1 else 1, ttype, inplace=inplace))
+        if inplace and d["inplace_unsupported"]:
+            continue
+        assert _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=(ttype == 2)) < TOL[fp] * 0.1
+
+
+def test_real_inplace_unsupported_flag(pkg):
+    # a CTA must own every m of a k slice for real in-place transforms (reference
+    # src/base/generator/small_batch_fft.cpp:38): with M beyond the lane count the plan refuses in-place
+    d = pkg.describe(pkg.make_config(1, [33, 4, 2], 4, pkg.FORWARD, pkg.R2C, inplace=True))
+    assert d["inplace_unsupported"]
+    d = pkg.describe(pkg.make_config(1, [16, 4, 2], 4, pkg.FORWARD, pkg.R2C, inplace=True))
+    assert not d["inplace_unsupported"]

@@ -1,0 +1,154 @@
+"""GPU tier: r2c / c2r parity through the C ABI (BASELINE config 3 and the reference's
+test/r2c.cpp cases), against the oracle, the reference's golden vectors and analytic signals."""
+import os
+
+import numpy as np
+import pytest
+
+from common import (C2R, R2C, TOL, addressed_mask, analytic_r2c, cdtype, rdtype, real_problem, reference_tol,
+                    rel_l2)
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _exec_bytes(pkg, cfg, x_np, out_dtype, nout, inplace):
+    """Run a plan on raw byte buffers (in-place plans view one buffer as both types)."""
+    plan = pkg.Plan(cfg, stream=_stream())
+    if inplace:
+        nbytes = max(x_np.nbytes, nout * np.dtype(out_dtype).itemsize)
+        raw = np.zeros(nbytes, np.uint8)
+        raw[: x_np.nbytes] = x_np.view(np.uint8)
+        d = torch.from_numpy(raw).cuda()
+        plan.execute(d)
+        torch.cuda.synchronize()
+        res = d.cpu().numpy().view(out_dtype)[:nout]
+    else:
+        xd = torch.from_numpy(x_np.view(np.uint8)).cuda()
+        yd = torch.zeros(nout * np.dtype(out_dtype).itemsize, dtype=torch.uint8, device="cuda")
+        plan.execute(xd, yd)
+        torch.cuda.synchronize()
+        res = yd.cpu().numpy().view(out_dtype)
+    names = plan.kernel_names
+    plan.close()
+    return res, names
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("ttype", [R2C, C2R])
+@pytest.mark.parametrize("M,N,K", [(1, 256, 1000), (1, 8, 333), (1, 30, 70), (16, 30, 33), (16, 64, 65), (4, 128, 20),
+                                   (3, 10, 50), (1, 15, 77), (2, 15, 51), (16, 27, 33), (5, 11, 40), (1, 105, 33),
+                                   (32, 102, 3), (3, 220, 33), (1, 2, 33), (1, 512, 20), (16, 500, 3), (1, 26, 65),
+                                   (3, 13, 65), (3, 110, 65)])
+def test_real_vs_oracle(pkg, oracle, fp, ttype, M, N, K):
+    rng = np.random.default_rng(ttype * 7919 + M * 131 + N * 17 + K)
+    d = -1 if ttype == R2C else 1
+    for inplace in (False, True):
+        cfg = pkg.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace)
+        if inplace and pkg.describe(cfg)["inplace_unsupported"]:
+            with pytest.raises(pkg.BadConfiguration):
+                # reference semantics: the plan exists, execute(in == out) throws
+                # (src/common/algorithm/small_batch_fft.hpp:107-110)
+                p = pkg.Plan(cfg, stream=_stream())
+                buf = torch.zeros(16, device="cuda")
+                p.execute(buf)
+            continue
+        ist, ost, x, odt, nout = real_problem(rng, pkg, ttype, M, N, K, fp, inplace, pollute=(ttype == C2R))
+        got, names = _exec_bytes(pkg, cfg, x, odt, nout, inplace)
+        ocfg = oracle.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace)
+        if inplace:
+            ref = np.zeros(max(x.nbytes, nout * np.dtype(odt).itemsize), np.uint8)
+            ref[: x.nbytes] = x.view(np.uint8)
+            oracle.dft(ocfg, ref)
+            want = ref.view(odt)[:nout]
+        else:
+            want = np.zeros(nout, odt)
+            oracle.dft(ocfg, x, want)
+        mask = addressed_mask(M, N // 2 + 1 if ttype == R2C else N, K, ost, nout)
+        assert rel_l2(got[mask], want[mask]) < TOL[fp], names
+        if not inplace:
+            assert np.all(got[~mask] == 0), names
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("M", [1, 3, 32])
+@pytest.mark.parametrize("N", [2, 4, 5, 8, 27, 16, 32, 128, 105, 256, 512, 102, 220, 10, 26])
+def test_r2c_analytic_reference_suite(pkg, fp, M, N):
+    """Port of reference test/r2c.cpp "r2c 1d out-of-place" (:182-190) and the c2r mirror
+    (:299-324, with polluted imag(X[0])): cosine <-> two deltas, tolerance 1e2*eps*sqrt(N)."""
+    for K in (1, 33):
+        x, X = analytic_r2c(M, N, K, fp)
+        tol = reference_tol(N, fp)
+        cfg = pkg.make_config(1, [M, N, K], fp, pkg.FORWARD, pkg.R2C, inplace=False)
+        got, names = _exec_bytes(pkg, cfg, np.ascontiguousarray(x).reshape(-1), cdtype(fp), X.size, False)
+        got = got.reshape(X.shape)
+        assert np.max(np.abs(got.real - X.real)) <= tol and np.max(np.abs(got.imag)) <= tol, names
+        # backward: the (polluted) spectrum gives back N * x
+        Xp = X.copy()
+        Xp[:, 0, :] += 1j * (1.0 + np.arange(M).reshape(1, M) + np.arange(K).reshape(K, 1))
+        cfg = pkg.make_config(1, [M, N, K], fp, pkg.BACKWARD, pkg.C2R, inplace=False)
+        back, names = _exec_bytes(pkg, cfg, np.ascontiguousarray(Xp).reshape(-1), rdtype(fp), x.size, False)
+        want = x.astype(np.float64) * N
+        assert np.max(np.abs(back.reshape(x.shape) - want)) <= tol * max(1.0, np.abs(want).max()), names
+
+
+def _golden_real():
+    if not os.path.exists(GOLDEN):
+        return []
+    z = np.load(GOLDEN)
+    return [str(n) for n in z["names"] if not str(n).startswith("c2c")]
+
+
+@pytest.mark.parametrize("name", _golden_real())
+def test_real_matches_reference_golden(pkg, name):
+    """Same inputs as the unmodified reference (emulated; tests/golden/make_golden.py), incl. the
+    in-place padded layouts and the polluted imag(X[0]) inputs."""
+    z = np.load(GOLDEN)
+    ttype, fp, d, M, N, K, inplace = [int(v) for v in z[name + "__meta"][:7]]
+    istride = [int(v) for v in z[name + "__meta"][7:10]]
+    ostride = [int(v) for v in z[name + "__meta"][10:13]]
+    cfg = pkg.make_config(1, [M, N, K], fp, d, ttype, istride=istride, ostride=ostride)
+    x = z[name + "__in"]
+    want = z[name + "__out"]
+    got, names = _exec_bytes(pkg, cfg, x, want.dtype, want.size, bool(inplace))
+    mask = addressed_mask(M, N // 2 + 1 if ttype == R2C else N, K, ostride, want.size)
+    assert rel_l2(got[mask], want[mask]) < TOL[fp], names
+
+
+@pytest.mark.parametrize("inplace", [False, True])
+def test_config3_full_size_round_trip(pkg, inplace):
+    """BASELINE config 3: fp32 N=256 M=1 K=2^20, r2c then c2r = N * identity (reference
+    test/r2c.cpp:375-497), in-place (padded rows of 258 floats) and out-of-place."""
+    N, K = 256, 1 << 20
+    row = 2 * (N // 2 + 1) if inplace else N
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    x = torch.zeros(K, row, dtype=torch.float32, device="cuda")
+    x[:, :N] = torch.rand(K, N, dtype=torch.float32, device="cuda", generator=g)
+    fwd = pkg.Plan(pkg.make_config(1, [1, N, K], 4, pkg.FORWARD, pkg.R2C, inplace=inplace), stream=_stream())
+    bwd = pkg.Plan(pkg.make_config(1, [1, N, K], 4, pkg.BACKWARD, pkg.C2R, inplace=inplace), stream=_stream())
+    if inplace:
+        buf = x.clone()
+        fwd.execute(buf)
+        torch.cuda.synchronize()
+        spec = torch.view_as_complex(buf.view(K, N // 2 + 1, 2)).clone()
+        bwd.execute(buf)
+        torch.cuda.synchronize()
+        back = buf[:, :N]
+    else:
+        spec = torch.empty(K, N // 2 + 1, dtype=torch.complex64, device="cuda")
+        back = torch.empty(K, N, dtype=torch.float32, device="cuda")
+        fwd.execute(x, spec)
+        bwd.execute(spec, back)
+        torch.cuda.synchronize()
+    ref = torch.fft.rfft(x[:4096, :N].double(), dim=1)
+    assert float((spec[:4096].to(torch.complex128) - ref).norm() / ref.norm()) < TOL[4]
+    assert float((back / N - x[:, :N]).norm() / x[:, :N].norm()) < TOL[4]
+    fwd.close()
+    bwd.close()
