@@ -37,8 +37,10 @@ static std::string translate_callbacks(user_module const &um, precision fp) {
     // (scalar -> vector broadcast, component-wise arithmetic).
     (void)fp;
     std::ostringstream os;
-    os << "namespace bbfft_ocl {\n"
-          "template <class T> struct vec2 {\n"
+    os << "#ifdef BBFFT_EMU\n#define __device__\n#endif\n"
+          "#define BBFFT_OCL_COMPAT 1\n"
+          "namespace bbfft_ocl {\n"
+          "template <class T> struct alignas(2 * sizeof(T)) vec2 {\n"
           "    T x, y;\n"
           "    __device__ vec2() {}\n"
           "    __device__ vec2(T a, T b) : x(a), y(b) {}\n"

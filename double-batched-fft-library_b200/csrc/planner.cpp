@@ -750,6 +750,7 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     os << "};\n} // namespace stub_" << identifier << "\n";
     os << "extern \"C\" BBK_GLOBAL void BBK_LAUNCH_BOUNDS(" << p.threads << ", " << p.min_blocks << ") "
        << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
+    os << "#ifdef BBFFT_OCL_COMPAT\n#undef float2\n#undef double2\n#undef BBFFT_OCL_COMPAT\n#endif\n";
     return os.str();
 }
 

@@ -7,6 +7,7 @@
 // check every index map of every planned kernel against the oracle before a GPU is involved.
 #ifndef BBFFT_CUDA_EMU_HPP
 #define BBFFT_CUDA_EMU_HPP
+#include <stddef.h>
 namespace bbfft_emu {
 struct thread_ctx {
     int tid;

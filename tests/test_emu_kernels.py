@@ -101,3 +101,47 @@ def test_real_inplace_unsupported_flag(pkg):
     assert d["inplace_unsupported"]
     d = pkg.describe(pkg.make_config(1, [16, 4, 2], 4, pkg.FORWARD, pkg.R2C, inplace=True))
     assert not d["inplace_unsupported"]
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("M,N", [(1, 8), (3, 12), (32, 8)])
+def test_callbacks_emulated_bit_identical(pkg, fp, M, N):
+    """Reference test/callback.cpp: a c2r plan with a zero-padding load callback and an r2c plan
+    with a truncate+scale store callback equal the plain plans on the padded / full problem
+    bit for bit (the FFT arithmetic is the same code; only the accessors differ)."""
+    from callbacks import load_zero_pad_opencl, store_truncate_scale_opencl
+    from common import cdtype, rdtype
+    K = 4
+    real = "float" if fp == 4 else "double"
+    rng = np.random.default_rng(3)
+    # ---- load callback (c2r of length 2N, upper half of the spectrum implied zero)
+    N_ext = 2 * N
+    ns_ref, ns = N_ext // 2 + 1, N // 2 + 1
+    X = (rng.uniform(0, 1, (K, ns, M)) + 1j * rng.uniform(0, 1, (K, ns, M))).astype(cdtype(fp))
+    X_ref = np.zeros((K, ns_ref, M), dtype=cdtype(fp))
+    X_ref[:, :ns, :] = X
+    strides = dict(istride=[1, M, M * ns_ref], ostride=[1, M, M * N_ext])
+    cfg_ref = pkg.make_config(1, [M, N_ext, K], fp, pkg.BACKWARD, pkg.C2R, **strides)
+    cfg = pkg.make_config(1, [M, N_ext, K], fp, pkg.BACKWARD, pkg.C2R,
+                          callbacks=(load_zero_pad_opencl(real, M, ns_ref, ns), "load", None, "opencl"), **strides)
+    x_ref = np.zeros(K * N_ext * M, dtype=rdtype(fp))
+    x = np.zeros_like(x_ref)
+    emu.run(cfg_ref, X_ref.reshape(-1), x_ref)
+    _, d = emu.run(cfg, X.reshape(-1), x)
+    assert d["identifier"].endswith("_load")
+    assert np.array_equal(x, x_ref)
+    # ---- store callback (r2c, keep N/4 rows scaled by 1/N)
+    N2 = 4 * N
+    ncut, nspec = N2 // 4, N2 // 2 + 1
+    xin = rng.uniform(0, 1, K * N2 * M).astype(rdtype(fp))
+    strides = dict(istride=[1, M, M * N2], ostride=[1, M, M * nspec])
+    cfg_ref = pkg.make_config(1, [M, N2, K], fp, pkg.FORWARD, pkg.R2C, **strides)
+    cfg = pkg.make_config(1, [M, N2, K], fp, pkg.FORWARD, pkg.R2C,
+                          callbacks=(store_truncate_scale_opencl(real, M, nspec, ncut, 1.0 / N2), None, "store", "opencl"),
+                          **strides)
+    Y_ref = np.zeros(K * nspec * M, dtype=cdtype(fp))
+    Y = np.zeros(K * ncut * M, dtype=cdtype(fp))
+    emu.run(cfg_ref, xin, Y_ref)
+    emu.run(cfg, xin, Y)
+    want = (Y_ref.reshape(K, nspec, M)[:, :ncut, :] * rdtype(fp)(1.0 / N2)).astype(cdtype(fp))
+    assert np.array_equal(Y.reshape(K, ncut, M), want)
