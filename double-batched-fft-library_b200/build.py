@@ -51,7 +51,7 @@ def embed_header():
 def build_host(verbose=False):
     inc = embed_header()
     srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]
-    hdrs = [inc] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".hpp")]
+    hdrs = [inc] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".hpp", ".inc"))]
     hdrs += [os.path.join(ROOT, "include", "bbfft_cuda.h"), os.path.join(ROOT, "include", "bbfft", "api.hpp")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -80,8 +80,29 @@ def build_host(verbose=False):
     return LIB
 
 
+def build_tools(verbose=False):
+    """bbfft-aot-generate / bbfft-offline-generate / bbfft-device-info (tools/native/bbfft_tools.cpp)."""
+    src = os.path.join(ROOT, "tools", "native", "bbfft_tools.cpp")
+    bindir = os.path.join(ROOT, "tools", "bin")
+    os.makedirs(bindir, exist_ok=True)
+    main = os.path.join(bindir, "bbfft-aot-generate")
+    if _newer(main, [src, LIB]):
+        cmd = [CXX, "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CUDA_HOME, "include"),
+               src, "-o", main, "-L" + HERE, "-lbbfft_cuda", "-Wl,-rpath," + HERE]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    for alias in ("bbfft-offline-generate", "bbfft-device-info"):
+        dst = os.path.join(bindir, alias)
+        if os.path.lexists(dst):
+            os.remove(dst)
+        os.symlink("bbfft-aot-generate", dst)
+    return bindir
+
+
 def build(verbose=False):
     build_host(verbose)
+    build_tools(verbose)
     from . import aot  # noqa: deferred, needs the library
     aot.build_builtin(verbose)
     return LIB
@@ -90,3 +111,4 @@ def build(verbose=False):
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     build_host(verbose=True)
+    build_tools(verbose=True)

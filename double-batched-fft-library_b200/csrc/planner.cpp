@@ -343,6 +343,26 @@ void choose_smem_layout(kernel_params &p) {
 } // namespace
 
 // ------------------------------------------------------------------------------------------
+// wisdom: planner overrides measured on the B200 by tools/tune_gpu.py (c2c, M = 16 sweep)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct wisdom_entry {
+    int fp, n;
+    char const *tune;
+};
+const wisdom_entry wisdom_table[] = {
+#include "wisdom.inc"
+    {0, 0, ""}};
+
+char const *wisdom_lookup(int fp, int n) {
+    for (auto const &w : wisdom_table) {
+        if (w.fp == fp && w.n == n) return w.tune;
+    }
+    return nullptr;
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
 kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
@@ -354,6 +374,21 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         throw std::runtime_error("bbfft-cuda planner: N too large for the single-kernel path");
     }
     auto tune = parse_tune(tune_str);
+    {
+        // measured wisdom applies to complex transforms whose batch rows fill the wisdom's lanes;
+        // explicit overrides win.  BBFFT_CUDA_NO_WISDOM=1 turns it off (used by the tuner).
+        char const *off = std::getenv("BBFFT_CUDA_NO_WISDOM");
+        char const *w = (prob.type == 0 && !(off && *off == '1')) ? wisdom_lookup(prob.fp, int(prob.N)) : nullptr;
+        if (w && *w) {
+            auto wt = parse_tune(w);
+            int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;
+            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
+                for (auto const &kv : wt) {
+                    if (!tune.count(kv.first)) tune[kv.first] = kv.second;
+                }
+            }
+        }
+    }
     kernel_plan plan;
     kernel_params &p = plan.p;
     p.fp = prob.fp;
@@ -449,7 +484,10 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         while (bh > 1 && std::uint64_t(bh / 2) >= kunits) bh /= 2;
     }
     p.BH = bh;
-    if (tune.count("BH")) p.BH = std::atoi(tune["BH"].c_str());
+    if (tune.count("BH")) {
+        p.BH = std::max(1, std::atoi(tune["BH"].c_str()));
+        while (p.BH > 1 && !p.klanes && std::uint64_t(p.BH / 2) >= kunits) p.BH /= 2;
+    }
     p.threads = p.ML * p.T * p.BH;
     if (p.threads > dev.max_threads_per_block) {
         throw std::runtime_error("bbfft-cuda planner: CTA too large");
