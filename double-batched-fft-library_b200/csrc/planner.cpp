@@ -138,8 +138,12 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
     double ideal = 0;
     for (int p : prime_factors(N)) ideal += radix_cost(p);
     // relax the register budget / thread limit until something fits
+    // Measured on B200 (profiles/r01_tuner_probe.json): two stages with large
+    // radices (18x18, 20x20, 14x25) beat three stages, so allow up to 32 (fp32) / 20 (fp64)
+    // complex elements per thread before adding a stage.
+    const int ebase = fp == 4 ? 32 : 20;
     for (int relax = 0; relax < 4 && best.radix.empty(); ++relax) {
-        const int emax = std::max(16 << relax, max_prime(N)); // complex elements per thread
+        const int emax = std::max(ebase << relax, max_prime(N)); // complex elements per thread
         const int tmax = max_threads_per_transform << relax;
         std::vector<std::vector<int>> facs;
         std::vector<int> cur;
@@ -169,7 +173,7 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
                 if (regs > emax) continue;
                 // cost: arithmetic (counting idle lanes) + exchange passes + mild preferences
                 // for ~8 elements per thread and for balanced radices
-                double cost = work / ideal + 0.35 * (L - 1);
+                double cost = work / ideal + 0.5 * (L - 1);
                 cost += 0.02 * std::abs(std::log2(double(regs) / 8.0));
                 cost += 0.001 * rsum;
                 if (cost < best.cost - 1e-9) {
@@ -539,7 +543,27 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     if (p.smem_bytes > dev.max_smem_per_block) {
         throw std::runtime_error("bbfft-cuda planner: shared memory demand too large");
     }
+    // Resident CTAs: a stage-synchronised CTA cannot overlap its own load and compute phases, so
+    // ask for 2-4 CTAs per SM whenever the register cap that implies still fits the butterflies.
     p.min_blocks = 1;
+    {
+        int regs_complex = 0;
+        for (int s = 0; s < p.L; ++s) {
+            int nsub = p.N / p.radix[s];
+            int cnt = (nsub + p.T - 1) / p.T;
+            regs_complex = std::max(regs_complex, (s == 0 ? cnt : 1) * p.radix[s]);
+        }
+        int need = (p.fp == 4 ? 2 : 4) * regs_complex + 24;
+        for (int mb = 4; mb >= 2; --mb) {
+            int cap = (dev.regs_per_sm / (((p.threads + 31) / 32 * 32) * mb)) / 8 * 8;
+            bool fits = cap >= need && p.threads * mb <= 2048 &&
+                        (p.smem_bytes + 1024) * std::size_t(mb) <= dev.smem_per_sm;
+            if (fits) {
+                p.min_blocks = mb;
+                break;
+            }
+        }
+    }
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
 
     // real in-place transforms need one CTA to own every m of a k slice, like the reference

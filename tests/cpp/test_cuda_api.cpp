@@ -1,0 +1,276 @@
+// tests/cpp/test_cuda_api.cpp -- device test of the C++ drop-in API (bbfft::configuration,
+// make_plan, plan::execute, jit_cache_all, aot_cache, generate_fft_kernels, callbacks) on CUDA.
+// Re-hosts the checks of the reference's device tests (test/c2c.cpp:17-127, test/r2c.cpp,
+// test/callback.cpp:18-114, test/error.cpp:13-21, examples/cache/main.cpp, examples/aot/main.cpp)
+// with cudaMalloc instead of sycl::malloc_device.  Built and run by tests/test_gpu_cpp_api.py.
+#include "bbfft/aot_cache.hpp"
+#include "bbfft/bad_configuration.hpp"
+#include "bbfft/configuration.hpp"
+#include "bbfft/cuda/device.hpp"
+#include "bbfft/cuda/make_plan.hpp"
+#include "bbfft/cuda/online_compiler.hpp"
+#include "bbfft/generator.hpp"
+#include "bbfft/jit_cache_all.hpp"
+
+#include <cuda_runtime_api.h>
+
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace bbfft;
+
+static int failures = 0;
+#define CHECK(cond)                                                                                \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            ++failures;                                                                            \
+            std::printf("CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond);                    \
+        }                                                                                          \
+    } while (0)
+#define CUDA_OK(x)                                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess) {                                                                   \
+            std::printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            std::exit(2);                                                                          \
+        }                                                                                          \
+    } while (0)
+
+template <typename T> double tol(std::size_t N) {
+    return 1e2 * std::numeric_limits<T>::epsilon() * std::sqrt(double(N)); // test/fft.hpp:17-19
+}
+
+template <typename T> struct device_vec {
+    T *p = nullptr;
+    std::size_t n;
+    explicit device_vec(std::size_t n_) : n(n_) { CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T))); }
+    ~device_vec() { cudaFree(p); }
+    void upload(std::vector<T> const &h) { CUDA_OK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice)); }
+    std::vector<T> download() const {
+        std::vector<T> h(n);
+        CUDA_OK(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
+        return h;
+    }
+};
+
+// test/c2c.cpp:17-51: single Fourier mode -> scaled Kronecker delta, in-place
+template <typename T> void c2c_analytic(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K, jit_cache *cache) {
+    const double tau = 6.28318530717958647692;
+    std::vector<std::complex<T>> x(M * N * K);
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t n = 0; n < N; ++n)
+            for (std::size_t m = 0; m < M; ++m) {
+                double arg = tau * double((m + k) % N) * double(n) / double(N);
+                double s = (1.0 + double(k) / double(K)) / double(N);
+                x[m + n * M + k * M * N] = {T(s * std::cos(arg)), T(s * std::sin(arg))};
+            }
+    device_vec<std::complex<T>> d(x.size());
+    d.upload(x);
+    configuration cfg = {1, {M, N, K}, to_precision_v<T>, direction::forward, transform_type::c2c};
+    auto plan = make_plan(cfg, stream, cache);
+    CHECK(bool(plan));
+    plan.execute(d.p).wait();
+    auto X = d.download();
+    double eps = tol<T>(N);
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t n = 0; n < N; ++n)
+            for (std::size_t m = 0; m < M; ++m) {
+                double ref = (n == (m + k) % N) ? 1.0 + double(k) / double(K) : 0.0;
+                auto v = X[m + n * M + k * M * N];
+                if (std::abs(v.real() - ref) > eps || std::abs(v.imag()) > eps) {
+                    ++failures;
+                    std::printf("c2c mismatch M=%zu N=%zu K=%zu at (%zu,%zu,%zu): %g %g vs %g\n", M, N, K, m, n, k,
+                                double(v.real()), double(v.imag()), ref);
+                    return;
+                }
+            }
+}
+
+// test/c2c.cpp:84-127: forward o backward = N * identity, out-of-place, with event dependencies
+template <typename T> void c2c_identity(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K) {
+    std::vector<std::complex<T>> x(M * N * K);
+    unsigned s = 12345;
+    for (auto &v : x) {
+        s = s * 1664525u + 1013904223u;
+        T a = T((s >> 8) & 0xffff) / T(65536);
+        s = s * 1664525u + 1013904223u;
+        v = {a, T((s >> 8) & 0xffff) / T(65536)};
+    }
+    device_vec<std::complex<T>> a(x.size()), b(x.size()), c(x.size());
+    a.upload(x);
+    configuration cf = {1, {M, N, K}, to_precision_v<T>, direction::forward, transform_type::c2c};
+    configuration cb = {1, {M, N, K}, to_precision_v<T>, direction::backward, transform_type::c2c};
+    auto pf = make_plan(cf, stream);
+    auto pb = make_plan(cb, stream);
+    auto e1 = pf.execute(a.p, b.p);
+    auto e2 = pb.execute(b.p, c.p, e1);
+    pb.execute(b.p, c.p, std::vector<cuda::event>{e1, e2}).wait();
+    auto y = c.download();
+    double err = 0, nrm = 0;
+    for (std::size_t i = 0; i < x.size(); ++i) {
+        err += std::norm(std::complex<double>(y[i]) / double(N) - std::complex<double>(x[i]));
+        nrm += std::norm(std::complex<double>(x[i]));
+    }
+    CHECK(std::sqrt(err / nrm) < (sizeof(T) == 4 ? 1e-5 : 1e-12));
+}
+
+// test/r2c.cpp: cosine -> two deltas (out-of-place), then c2r with polluted imag(X[0]) (:310-324)
+template <typename T> void r2c_c2r(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K) {
+    const double tau = 6.28318530717958647692;
+    std::size_t Nh = N / 2 + 1;
+    std::vector<T> x(M * N * K);
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t n = 0; n < N; ++n)
+            for (std::size_t m = 0; m < M; ++m)
+                x[m + n * M + k * M * N] = T((1.0 + double(k) / K) * std::cos(tau * double((m + k) % N) * double(n) / N) / N);
+    device_vec<T> dx(x.size()), dback(x.size());
+    device_vec<std::complex<T>> dX(M * Nh * K);
+    dx.upload(x);
+    configuration cfg = {1, {M, N, K}, to_precision_v<T>, direction::forward, transform_type::r2c};
+    cfg.set_strides_default(false);
+    make_plan(cfg, stream).execute(dx.p, dX.p).wait();
+    auto X = dX.download();
+    double eps = tol<T>(N);
+    bool ok = true;
+    for (std::size_t k = 0; k < K && ok; ++k)
+        for (std::size_t n = 0; n < Nh && ok; ++n)
+            for (std::size_t m = 0; m < M && ok; ++m) {
+                long b = long((m + k) % N);
+                double ref = ((long(n) - b) % long(N) == 0 ? 0.5 : 0.0) + ((long(n) + b) % long(N) == 0 ? 0.5 : 0.0);
+                ref *= 1.0 + double(k) / K;
+                auto v = X[m + n * M + k * M * Nh];
+                ok = std::abs(v.real() - ref) <= eps && std::abs(v.imag()) <= eps;
+            }
+    CHECK(ok);
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t m = 0; m < M; ++m) X[m + k * M * Nh].imag(T(1.0 + m + k)); // pollute
+    dX.upload(X);
+    configuration cb = {1, {M, N, K}, to_precision_v<T>, direction::backward, transform_type::c2r};
+    cb.set_strides_default(false);
+    make_plan(cb, stream).execute(dX.p, dback.p).wait();
+    auto back = dback.download();
+    ok = true;
+    for (std::size_t i = 0; i < x.size() && ok; ++i) ok = std::abs(double(back[i]) - double(x[i]) * N) <= eps * 2;
+    CHECK(ok);
+}
+
+int main() {
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) {
+        std::printf("no CUDA device\n");
+        return 2;
+    }
+    cudaStream_t stream;
+    CUDA_OK(cudaStreamCreate(&stream));
+    auto info = get_device_info(0);
+    std::printf("device_info %s id %llx\n", info.to_string().c_str(), (unsigned long long)get_device_id(0));
+    CHECK(info.max_work_group_size == 1024);
+    CHECK(info.subgroup_sizes.size() == 1 && info.subgroup_sizes[0] == 32);
+
+    // --- c2c analytic, reference size lists (test/c2c.cpp:56-59), shared jit cache
+    jit_cache_all cache;
+    for (std::size_t M : {1u, 3u, 16u, 17u, 64u})
+        for (std::size_t N : {2u, 3u, 5u, 7u, 11u, 13u, 4u, 8u, 16u, 32u, 128u, 256u, 512u, 27u, 63u, 105u, 363u})
+            for (std::size_t K : {1u, 32u}) {
+                c2c_analytic<float>(stream, M, N, K, &cache);
+                c2c_analytic<double>(stream, M, N, K, &cache);
+            }
+    std::size_t cached = cache.kernel_names().size();
+    CHECK(cached > 0);
+    // examples/cache/main.cpp:50-52: a plan that differs only in K re-uses the cached kernel
+    c2c_analytic<float>(stream, 16, 128, 77, &cache);
+    CHECK(cache.kernel_names().size() == cached);
+    c2c_identity<float>(stream, 16, 200, 40);
+    c2c_identity<double>(stream, 3, 343, 9);
+
+    // --- real transforms
+    for (std::size_t M : {1u, 3u, 32u})
+        for (std::size_t N : {2u, 4u, 5u, 8u, 27u, 16u, 128u, 105u, 256u, 102u, 26u}) {
+            r2c_c2r<float>(stream, M, N, 33);
+            r2c_c2r<double>(stream, M, N, 33);
+        }
+
+    // --- errors (test/error.cpp:13-21, small_batch_fft.hpp:107-110)
+    for (unsigned dim : {0u, 4u}) {
+        bool thrown = false;
+        try {
+            configuration cfg = {dim, {1, 8, 1}, precision::f32};
+            make_plan(cfg, stream);
+        } catch (bad_configuration const &) {
+            thrown = true;
+        }
+        CHECK(thrown);
+    }
+    {
+        configuration cfg = {1, {64, 8, 4}, precision::f32, direction::forward, transform_type::r2c};
+        auto plan = make_plan(cfg, stream); // creation succeeds, in-place execute throws
+        device_vec<float> buf(64 * 10 * 4);
+        bool thrown = false;
+        try {
+            plan.execute(buf.p);
+        } catch (bad_configuration const &) {
+            thrown = true;
+        }
+        CHECK(thrown);
+    }
+
+    // --- AOT: generate_fft_kernels -> cubin -> aot_cache (examples/aot/main.cpp:58-73)
+    {
+        configuration cfg = {1, {16, 48, 10}, precision::f64, direction::backward, transform_type::c2c};
+        std::ostringstream src;
+        auto names = generate_fft_kernels(src, {cfg}, info);
+        CHECK(names.size() == 1);
+        auto bin = cuda::compile_to_native(src.str());
+        aot_cache aot;
+        aot.register_module(cuda::create_aot_module(bin.data(), bin.size(), module_format::native, 0));
+        CHECK(bool(aot.get({names[0], get_device_id(0)})));
+        CHECK(!aot.get({"no_such_kernel", get_device_id(0)}));
+        auto plan = make_plan(cfg, stream, &aot);
+        device_vec<std::complex<double>> d(16 * 48 * 10);
+        std::vector<std::complex<double>> h(d.n, {1.0, 0.0});
+        d.upload(h);
+        plan.execute(d.p).wait();
+        auto r = d.download();
+        CHECK(std::abs(r[0].real() - 48.0) < 1e-12 && std::abs(r[16].real()) < 1e-12);
+    }
+
+    // --- 3d plan + callback (OpenCL-C source as in test/callback.cpp:151-158) smoke
+    {
+        configuration cfg = {3, {1, 8, 4, 6, 2}, precision::f32, direction::forward, transform_type::c2c};
+        auto plan = make_plan(cfg, stream);
+        device_vec<std::complex<float>> d(8 * 4 * 6 * 2);
+        std::vector<std::complex<float>> h(d.n, {1.0f, 0.0f});
+        d.upload(h);
+        plan.execute(d.p).wait();
+        auto r = d.download();
+        CHECK(std::abs(r[0].real() - 192.0f) < 1e-3f && std::abs(r[1].real()) < 1e-3f);
+        char const src[] = "void store(global float2* out, size_t offset, float2 value) { out[offset] = value * 0.5f; }";
+        configuration cc = {1, {4, 16, 3}, precision::f32, direction::forward, transform_type::c2c};
+        cc.callbacks = {src, sizeof(src) - 1, nullptr, "store"};
+        auto pc = make_plan(cc, stream);
+        device_vec<std::complex<float>> e(4 * 16 * 3);
+        std::vector<std::complex<float>> he(e.n, {1.0f, 0.0f});
+        e.upload(he);
+        pc.execute(e.p).wait();
+        auto rc = e.download();
+        CHECK(rc[0].real() == 8.0f);
+        bool thrown = false;
+        try {
+            cfg.callbacks = cc.callbacks;
+            make_plan(cfg, stream); // callbacks are 1d only (nd_fft.hpp:29-31)
+        } catch (bad_configuration const &) {
+            thrown = true;
+        }
+        CHECK(thrown);
+    }
+    cudaStreamDestroy(stream);
+    std::printf("%s (%d failures)\n", failures ? "FAILED" : "OK", failures);
+    return failures ? 1 : 0;
+}

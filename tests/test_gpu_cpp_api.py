@@ -1,0 +1,38 @@
+"""The C++ drop-in API exercised from compiled user code (tests/cpp/test_cuda_api.cpp): compiled
+in the CPU tier, executed on the GPU tier."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "double-batched-fft-library_b200")
+EXE = os.path.join(ROOT, "tests", "cpp", "test_cuda_api")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+
+def _build():
+    src = os.path.join(ROOT, "tests", "cpp", "test_cuda_api.cpp")
+    deps = [src, os.path.join(LIBDIR, "libbbfft_cuda.so")]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(CUDA_HOME, "include"), src, "-o", EXE, "-L" + LIBDIR, "-lbbfft_cuda",
+                           "-L" + os.path.join(CUDA_HOME, "lib64"), "-lcudart_static", "-ldl", "-lrt", "-lpthread",
+                           "-Wl,-rpath," + LIBDIR])
+
+
+def test_cpp_api_user_code_compiles(pkg):
+    """User code written against the reference's headers (configuration aggregate init,
+    make_plan, execute overloads, caches, generator) builds against include/bbfft."""
+    _build()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_cpp_api_on_device(pkg):
+    _build()
+    r = subprocess.run([EXE], capture_output=True, text=True, timeout=1500)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
