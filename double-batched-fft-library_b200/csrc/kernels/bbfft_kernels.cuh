@@ -34,12 +34,14 @@
 #define BBK_RESTRICT __restrict__
 #define BBK_GLOBAL
 #define BBK_LAUNCH_BOUNDS(t, b)
+#define BBK_MAXNREG(r)
 #else
 #define BBK_DEV __device__ __forceinline__
 #define BBK_HD __host__ __device__ __forceinline__
 #define BBK_CE __host__ __device__ constexpr
 #define BBK_GLOBAL __global__
 #define BBK_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+#define BBK_MAXNREG(r) __maxnreg__(r)
 #define BBK_RESTRICT __restrict__
 #endif
 
@@ -73,11 +75,28 @@ template <class T> struct alignas(2 * sizeof(T)) cx {
     T x, y;
 };
 
+// Every floating-point multiply of the transform is written with an explicit-rounding intrinsic
+// (never a bare `*`), so the compiler cannot contract or split multiply-adds differently from
+// one instantiation to the next: a plan with user callbacks, the same plan without, the
+// NVRTC-compiled and the nvcc-compiled kernel all produce bit-identical spectra
+// (the reference's test/callback.cpp:102-104,186-192 compares with ==).
+#ifdef BBFFT_EMU
+template <class T> BBK_DEV T fmul(T a, T b) { return a * b; }
+template <class T> BBK_DEV T ffma(T a, T b, T c) { return a * b + c; }
+#else
+BBK_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
+BBK_DEV double fmul(double a, double b) { return __dmul_rn(a, b); }
+BBK_DEV float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+BBK_DEV double ffma(double a, double b, double c) { return __fma_rn(a, b, c); }
+#endif
+
 template <class T> BBK_DEV cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
 template <class T> BBK_DEV cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
 template <class T> BBK_DEV cx<T> cmul(cx<T> a, cx<T> b) {
-    return cx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+    return cx<T>{ffma(a.x, b.x, -fmul(a.y, b.y)), ffma(a.x, b.y, fmul(a.y, b.x))};
 }
+// real scalar times complex
+template <class T> BBK_DEV cx<T> rmul(cx<T> a, T s) { return cx<T>{fmul(a.x, s), fmul(a.y, s)}; }
 template <class T> BBK_DEV cx<T> conj(cx<T> a) { return cx<T>{a.x, -a.y}; }
 // multiply by DIR*i  (= exp(DIR*i*pi/2))
 template <int DIR, class T> BBK_DEV cx<T> mul_i(cx<T> a) {
@@ -142,7 +161,7 @@ template <class T, class W, int R, int K, int DIR> BBK_DEV cx<T> mul_w(cx<T> a) 
         // (a.x + i a.y)(cr + i ci) = (cr a.x - ci a.y) + i (ci a.x + cr a.y)
         T re = (cr > 0 ? a.x : -a.x) - (ci > 0 ? a.y : -a.y);
         T im = (ci > 0 ? a.x : -a.x) + (cr > 0 ? a.y : -a.y);
-        return cx<T>{re * h, im * h};
+        return cx<T>{fmul(re, h), fmul(im, h)};
     } else {
         return cmul(a, twc<T, W, R, k, DIR>());
     }
@@ -177,14 +196,14 @@ template <class T, class W, int R, int DIR> struct bfly {
                 constexpr int idx = (j * k) % R * (W::n / R);
                 constexpr T c = T(W::c(idx));
                 constexpr T sn = T(W::s(idx));
-                re.x += c * s[j].x;
-                re.y += c * s[j].y;
+                re.x = ffma(c, s[j].x, re.x);
+                re.y = ffma(c, s[j].y, re.y);
                 if constexpr (j == 1) {
-                    im.x = sn * d[j].x;
-                    im.y = sn * d[j].y;
+                    im.x = fmul(sn, d[j].x);
+                    im.y = fmul(sn, d[j].y);
                 } else {
-                    im.x += sn * d[j].x;
-                    im.y += sn * d[j].y;
+                    im.x = ffma(sn, d[j].x, im.x);
+                    im.y = ffma(sn, d[j].y, im.y);
                 }
             });
             cx<T> rot = mul_i<DIR>(im); // DIR * i * im
@@ -224,8 +243,8 @@ template <class T, class W, int DIR> struct bfly<T, W, 8, DIR> {
         cx<T> b3 = v[3] + v[7], c3 = v[3] - v[7];
         // w8^1 = (1 + DIR i)/sqrt2 ; w8^3 = (-1 + DIR i)/sqrt2
         cx<T> r1 = mul_i<DIR>(c1), r3 = mul_i<DIR>(c3);
-        c1 = cx<T>{(c1.x + r1.x) * h, (c1.y + r1.y) * h};
-        c3 = cx<T>{(r3.x - c3.x) * h, (r3.y - c3.y) * h};
+        c1 = cx<T>{fmul(c1.x + r1.x, h), fmul(c1.y + r1.y, h)};
+        c3 = cx<T>{fmul(r3.x - c3.x, h), fmul(r3.y - c3.y, h)};
         // even outputs: radix-4 on b, odd outputs: radix-4 on c
         cx<T> e0 = b0 + b2, e1 = b0 - b2, e2 = b1 + b3, e3 = mul_i<DIR>(b1 - b3);
         cx<T> o0 = c0 + c2, o1 = c0 - c2, o2 = c1 + c3, o3 = mul_i<DIR>(c1 - c3);
@@ -635,8 +654,8 @@ template <class C> BBK_DEV void fft1d(args const &a) {
                 const cx<T> y2 = conj(sm[p2]);
                 const cx<T> w = ldg_cx(twr + i);
                 const cx<T> iw = cx<T>{-w.y, w.x};
-                const cx<T> aa = cx<T>{(y2.x + y1.x) * T(0.5), (y2.y + y1.y) * T(0.5)};
-                const cx<T> bb = cmul(cx<T>{(y2.x - y1.x) * T(0.5), (y2.y - y1.y) * T(0.5)}, iw);
+                const cx<T> aa = rmul(y2 + y1, T(0.5));
+                const cx<T> bb = cmul(rmul(y2 - y1, T(0.5)), iw);
                 const cx<T> xi = aa + bb;
                 const cx<T> xh = conj(aa - bb);
                 if constexpr (C::STORE_STAGED) {
@@ -723,8 +742,8 @@ template <class C> BBK_DEV void fft1d(args const &a) {
             if (i < PAIRS && okp) {
                 const cx<T> y1 = sm[G::soff(b, pos_of_bin<C>(i))];
                 const cx<T> y2 = conj(sm[G::soff(b, pos_of_bin<C>((C::N - i) % C::N))]);
-                const cx<T> av = cx<T>{(y2.x + y1.x) * T(0.5), (y2.y + y1.y) * T(0.5)};
-                const cx<T> d = cx<T>{(y2.x - y1.x) * T(0.5), (y2.y - y1.y) * T(0.5)};
+                const cx<T> av = rmul(y2 + y1, T(0.5));
+                const cx<T> d = rmul(y2 - y1, T(0.5));
                 const cx<T> bv = cx<T>{-d.y, d.x}; // i * d
                 const u64 o = m + u64(i) * C::os1(a) + (2 * k) * C::os2(a);
                 C::st(a.out, o, av);

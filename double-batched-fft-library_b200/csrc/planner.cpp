@@ -49,6 +49,16 @@ static int pow2_ceil(std::uint64_t x) {
     return p;
 }
 
+// Largest per-thread register count with which `blocks` CTAs of `threads` threads are resident on
+// one SM: the 64K-register file is four 16K partitions, a CTA's warps are dealt round-robin over
+// them, and registers are allocated per warp in multiples of 8 per thread.
+int reg_cap(int threads, int blocks) {
+    int warps = (threads + 31) / 32;
+    int per_partition = std::max(1, blocks) * ((warps + 3) / 4);
+    int cap = (16384 / per_partition / 32) / 8 * 8;
+    return std::max(24, std::min(cap, 255));
+}
+
 std::uint64_t kernel_params::k_per_cta() const {
     std::uint64_t per = klanes ? std::uint64_t(ML) * BH : std::uint64_t(BH);
     if (mode == k_r2c_double || mode == k_c2r_double) per *= 2;
@@ -545,6 +555,9 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     }
     // Resident CTAs: a stage-synchronised CTA cannot overlap its own load and compute phases, so
     // ask for 2-4 CTAs per SM whenever the register cap that implies still fits the butterflies.
+    // The cap is exact (reg_cap models the four register-file partitions of an SM) and is given to
+    // the compiler as __maxnreg__, so the occupancy is a planner decision and not an accident of
+    // the register allocator (NVRTC and nvcc differ by a few registers on the same source).
     p.min_blocks = 1;
     {
         int regs_complex = 0;
@@ -553,10 +566,11 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
             int cnt = (nsub + p.T - 1) / p.T;
             regs_complex = std::max(regs_complex, (s == 0 ? cnt : 1) * p.radix[s]);
         }
-        int need = (p.fp == 4 ? 2 : 4) * regs_complex + 24;
+        // measured: unconstrained kernels use ~1.6 registers per live 32-bit word + 20
+        int words = (p.fp == 4 ? 2 : 4) * regs_complex;
+        int need = words + words / 4 + 32;
         for (int mb = 4; mb >= 2; --mb) {
-            int cap = (dev.regs_per_sm / (((p.threads + 31) / 32 * 32) * mb)) / 8 * 8;
-            bool fits = cap >= need && p.threads * mb <= 2048 &&
+            bool fits = reg_cap(p.threads, mb) >= need && p.threads * mb <= 2048 &&
                         (p.smem_bytes + 1024) * std::size_t(mb) <= dev.smem_per_sm;
             if (fits) {
                 p.min_blocks = mb;
@@ -565,6 +579,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         }
     }
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
+    p.max_regs = reg_cap(p.threads, p.min_blocks);
 
     // real in-place transforms need one CTA to own every m of a k slice, like the reference
     // (src/base/generator/small_batch_fft.cpp:38, factor2_slm_fft.cpp:63)
@@ -810,7 +825,7 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     os << "    static constexpr bool HAS_CALLBACKS = "
        << ((p.cb_load.empty() && p.cb_store.empty()) ? "false" : "true") << ";\n";
     os << "};\n} // namespace stub_" << identifier << "\n";
-    os << "extern \"C\" BBK_GLOBAL void BBK_LAUNCH_BOUNDS(" << p.threads << ", " << p.min_blocks << ") "
+    os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") "
        << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
     os << "#ifdef BBFFT_OCL_COMPAT\n#undef float2\n#undef double2\n#undef BBFFT_OCL_COMPAT\n#endif\n";
     return os.str();

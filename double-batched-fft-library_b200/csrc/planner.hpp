@@ -50,7 +50,8 @@ struct kernel_params {
     int LL = 1, PADK = 0, ROW = 1;
     std::size_t smem_bytes = 0;
     int threads = 1;
-    int min_blocks = 1;
+    int min_blocks = 1; // resident CTAs per SM the register cap is sized for
+    int max_regs = 255;  // __maxnreg__ of the kernel (reg_cap(threads, min_blocks))
     std::string cb_load, cb_store;
 
     int batch_per_cta() const { return ML * BH; }
@@ -59,6 +60,9 @@ struct kernel_params {
     // k slices consumed per CTA (for odd-N real transforms a slice pair counts as one unit)
     std::uint64_t k_per_cta() const;
 };
+
+// register cap for `blocks` resident CTAs of `threads` threads (four register-file partitions)
+int reg_cap(int threads, int blocks);
 
 struct kernel_plan {
     kernel_params p;
