@@ -33,6 +33,9 @@ BUILTIN_DESCRIPTORS = (
     ["scfo64*16384"]
     + ["scfo16.%d*%d" % (n, sweep_k(n, 4)) for n in smooth_sizes()]
     + ["dcfo16.%d*%d" % (n, sweep_k(n, 8)) for n in smooth_sizes()]
+    # config 3: r2c / c2r N=256, K=2^20, in- and out-of-place; config 4: 3d fp64 64^3, 2d fp32 128^2
+    + ["srfo256*1048576", "srfi256*1048576", "srbo256*1048576", "srbi256*1048576"]
+    + ["dcfo64x64x64*64", "scfo128x128*64"]
 )
 
 

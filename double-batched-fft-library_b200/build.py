@@ -92,6 +92,16 @@ def build_tools(verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
+    # native benchmark driver with cuFFT beside it (benchmark/main-cuda.cu)
+    bench_src = os.path.join(ROOT, "benchmark", "main-cuda.cu")
+    bench = os.path.join(bindir, "bbfft-bench")
+    if os.path.exists(bench_src) and _newer(bench, [bench_src, LIB]):
+        cmd = [NVCC, "-std=c++17", "-O2", "-lineinfo", "-ccbin", CXX] + ARCH_FLAGS + [
+            "-I" + os.path.join(ROOT, "include"), bench_src, "-o", bench, "-L" + HERE, "-lbbfft_cuda", "-lcufft",
+            "-Xlinker", "-rpath," + HERE]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
     for alias in ("bbfft-offline-generate", "bbfft-device-info"):
         dst = os.path.join(bindir, alias)
         if os.path.lexists(dst):

@@ -77,6 +77,7 @@ def lib():
         l.bbfft_cuda_plan_kernel_name.restype = C.c_char_p
         l.bbfft_cuda_plan_kernel_name.argtypes = [C.c_void_p, C.c_int]
         l.bbfft_cuda_plan_num_kernels.argtypes = [C.c_void_p]
+        l.bbfft_cuda_plan_launches.argtypes = [C.c_void_p]
         l.bbfft_cuda_kernel_header.restype = C.c_char_p
         l.bbfft_cuda_default_strides.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(C.c_size_t),
                                                  C.POINTER(C.c_size_t)]
@@ -179,7 +180,7 @@ def describe(cfg, tune=""):
             smem_bytes=int(d.smem_bytes),
             inplace_unsupported=bool(d.inplace_unsupported),
             fp=int(d.fp),
-            radix=list(d.radix)[: d.n_stages],
+            radix=list(d.radix)[: min(4, d.n_stages)],
             threads_per_transform=int(d.threads_per_transform),
             batch_lanes=int(d.batch_lanes),
             batch_high=int(d.batch_high),
@@ -270,7 +271,7 @@ class Plan:
 
     @property
     def launches_per_execute(self):
-        return lib().bbfft_cuda_plan_num_kernels(self._p)
+        return lib().bbfft_cuda_plan_launches(self._p)
 
     def execute(self, inp, out=None, stream=None):
         """Asynchronous, stream-ordered.  out=None (or out is inp) -> in-place."""

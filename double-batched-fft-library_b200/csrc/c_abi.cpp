@@ -192,11 +192,7 @@ int bbfft_cuda_plan_create_tuned(bbfft_cuda_plan_t *plan, const bbfft_cuda_confi
         } else {
             p->impl = cuda::select_fft_algorithm(c, a, jc);
         }
-        if (auto one = std::dynamic_pointer_cast<cuda::fft1d_plan>(p->impl)) {
-            p->kernel_names.push_back(one->kernel().identifier);
-        } else if (auto nd = std::dynamic_pointer_cast<cuda::nd_plan>(p->impl)) {
-            for (auto const &q : nd->passes()) p->kernel_names.push_back(q->kernel().identifier);
-        }
+        if (auto pb = std::dynamic_pointer_cast<cuda::plan_base>(p->impl)) pb->kernel_names(p->kernel_names);
         *plan = p.release();
     });
 }
@@ -268,6 +264,10 @@ int bbfft_cuda_plan_destroy(bbfft_cuda_plan_t plan) {
 
 int bbfft_cuda_plan_num_kernels(bbfft_cuda_plan_t plan) { return plan ? int(plan->kernel_names.size()) : 0; }
 
+int bbfft_cuda_plan_launches(bbfft_cuda_plan_t plan) {
+    return plan && plan->impl ? int(plan->impl->launches_per_execute()) : 0;
+}
+
 const char *bbfft_cuda_plan_kernel_name(bbfft_cuda_plan_t plan, int index) {
     if (!plan || index < 0 || index >= int(plan->kernel_names.size())) return "";
     return plan->kernel_names[index].c_str();
@@ -277,7 +277,30 @@ int bbfft_cuda_describe(const bbfft_cuda_config *cfg, const char *tune, bbfft_cu
     return guarded([&] {
         std::memset(desc, 0, sizeof(*desc));
         auto c = to_cpp(*cfg);
-        if (c.dim != 1) throw bad_configuration("bbfft_cuda_describe handles 1d configurations");
+        if (c.dim == 2) {
+            // fused 2d tile kernel (the only single-kernel 2d plan)
+            auto steps = cuda::nd_decompose(c, cuda::device_props{});
+            if (steps.size() != 1 || !steps[0].fused) {
+                throw bad_configuration("bbfft_cuda_describe: this 2d configuration is not a single fused kernel");
+            }
+            auto tp = cuda::plan_kernel_2d(steps[0].tile, cuda::device_props{}, tune ? tune : "");
+            desc->identifier = dup_string(tp.identifier);
+            desc->source = dup_string(tp.source);
+            desc->twiddle_len = tp.twiddle.size();
+            desc->twiddle = static_cast<double *>(std::malloc(sizeof(double) * tp.twiddle.size()));
+            std::memcpy(desc->twiddle, tp.twiddle.data(), sizeof(double) * tp.twiddle.size());
+            desc->grid = steps[0].tile.K;
+            desc->threads = tp.p.threads;
+            desc->smem_bytes = tp.p.smem_bytes;
+            desc->fp = tp.p.fp;
+            desc->n_stages = tp.p.a.L + tp.p.b.L;
+            for (int s = 0; s < 4; ++s) desc->radix[s] = tp.p.a.radix[s];
+            desc->threads_per_transform = tp.p.threads;
+            desc->batch_lanes = tp.p.PADK;
+            desc->batch_high = tp.p.min_blocks;
+            return;
+        }
+        if (c.dim != 1) throw bad_configuration("bbfft_cuda_describe handles 1d and fused 2d configurations");
         auto kp = cuda::plan_kernel_1d(cuda::to_problem(c), cuda::device_props{}, tune ? tune : "");
         desc->identifier = dup_string(kp.identifier);
         desc->source = dup_string(kp.source);

@@ -778,6 +778,136 @@ template <class C> BBK_DEV void fft1d(args const &a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused 2d c2c transform ("tile kernel").  One CTA owns one M x N1 x N2 tile -- contiguous in
+// global memory for the default layout, element (m, n1, n2) at m + M*n1 + M*N1*n2 -- keeps it in
+// shared memory across both passes and touches HBM exactly once on the way in and once on the
+// way out.  Replaces two of the chained double-batched 1d launches of the reference's nd_fft
+// (src/common/algorithm/nd_fft.hpp:66-112, 140-152) when the tile fits into shared memory.
+//
+// Traits contract (generated): real_t, DIR, THREADS, PADK, TILE_STRIDE (elements between tiles),
+// ld/st hooks and two pass descriptors PA (axis n1) and PB (axis n2), each with
+//   N  transform length           S  element stride of the axis inside the tile
+//   O  repeats of the S*N block   L, radix(s), tw_off(s), WR<s>  as for the 1d kernel.
+// Every stage deals its S*(N/R)*O sub-FFTs round-robin to all THREADS threads with the
+// unit-stride index fastest, so global accesses coalesce and shared-memory accesses are (after
+// the planner's padding search) conflict-free.  Stages are in place; the last stage of pass A
+// writes through the digit reversal ("sorted") so that pass B sees natural order -- every thread
+// holds its sub-FFTs in registers across one extra barrier instead of a second tile buffer.
+// ------------------------------------------------------------------------------------------
+enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2 };
+
+template <class C> BBK_DEV int tile_phys(int lin) {
+    if constexpr (C::PADK > 0) {
+        return lin + lin / C::PADK;
+    } else {
+        return lin;
+    }
+}
+
+template <class P> BBK_CE int pass_ns(int s) {
+    int n = P::N;
+    for (int i = 0; i < s; ++i) n /= P::radix(i);
+    return n;
+}
+
+template <class C, class P, int S, int SRC, int DST>
+BBK_DEV void tile_stage(args const &a, cx<typename C::real_t> *sm, u64 gbase, int tid) {
+    using T = typename C::real_t;
+    constexpr int R = P::radix(S);
+    constexpr int NS = pass_ns<P>(S);
+    constexpr int NS1 = NS / R;
+    constexpr int NSUB = P::N / R;
+    constexpr int TOTAL = P::S * NSUB * P::O;
+    constexpr int CNT = (TOTAL + C::THREADS - 1) / C::THREADS;
+    constexpr bool LAST = (S == P::L - 1);
+    static_assert(DST == T_SMEM || LAST, "only a pass's last stage leaves the in-place scheme");
+    using WR = typename P::template WR<S>;
+    const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + P::tw_off(S);
+
+    cx<T> v[CNT][R];
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int id = tid + C::THREADS * i;
+        if (TOTAL % C::THREADS == 0 || id < TOTAL) {
+            const int lo = id % P::S, r = id / P::S;
+            const int u = r % NSUB, hi = r / NSUB;
+            const int base = lo + P::S * ((u / NS1) * NS + u % NS1) + P::S * P::N * hi;
+            static_for<0, R>([&](auto jj) {
+                constexpr int j = decltype(jj)::value;
+                const int lin = base + P::S * NS1 * j;
+                if constexpr (SRC == T_GLOBAL) {
+                    v[i][j] = C::ld(a.in, gbase + u64(lin));
+                } else {
+                    v[i][j] = sm[tile_phys<C>(lin)];
+                }
+            });
+        }
+    });
+    if constexpr (DST == T_SMEM_SORTED && SRC != T_GLOBAL) {
+        BBK_SYNC(); // every read of the stage happens before its out-of-place writes
+    }
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int id = tid + C::THREADS * i;
+        if (TOTAL % C::THREADS == 0 || id < TOTAL) {
+            const int lo = id % P::S, r = id / P::S;
+            const int u = r % NSUB, hi = r / NSUB;
+            reg_fft<T, WR, R, C::DIR>::run(v[i]);
+            if constexpr (!LAST) {
+                const int n2 = u % NS1;
+                static_for<1, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    v[i][q] = cmul(v[i][q], ldg_cx(tw + (q - 1) * NS1 + n2));
+                });
+            }
+            if constexpr (DST == T_SMEM) {
+                const int base = lo + P::S * ((u / NS1) * NS + u % NS1) + P::S * P::N * hi;
+                static_for<0, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    sm[tile_phys<C>(base + P::S * NS1 * q)] = v[i][q];
+                });
+            } else {
+                const int base = lo + P::S * bin_of_sub<P>(u) + P::S * P::N * hi;
+                static_for<0, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    const int lin = base + P::S * (P::N / R) * q;
+                    if constexpr (DST == T_GLOBAL) {
+                        C::st(a.out, gbase + u64(lin), v[i][q]);
+                    } else {
+                        sm[tile_phys<C>(lin)] = v[i][q];
+                    }
+                });
+            }
+        }
+    });
+}
+
+template <class C, class P, int S, int SRC0, int DSTL>
+BBK_DEV void tile_pass(args const &a, cx<typename C::real_t> *sm, u64 gbase, int tid) {
+    if constexpr (S < P::L) {
+        constexpr int SRC = (S == 0) ? SRC0 : T_SMEM;
+        constexpr int DST = (S == P::L - 1) ? DSTL : T_SMEM;
+        if constexpr (S > 0) {
+            BBK_SYNC();
+        }
+        tile_stage<C, P, S, SRC, DST>(a, sm, gbase, tid);
+        tile_pass<C, P, S + 1, SRC0, DSTL>(a, sm, gbase, tid);
+    }
+}
+
+template <class C> BBK_DEV void fft2d_tile(args const &a) {
+    using T = typename C::real_t;
+    cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const u64 tile = BBK_BID();
+    if (tile >= a.K) return;
+    const u64 gbase = tile * u64(C::TILE_STRIDE);
+    tile_pass<C, typename C::PA, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, gbase, tid);
+    BBK_SYNC();
+    tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL>(a, sm, gbase, tid);
+}
+
 } // namespace bbk
 
 #endif // BBFFT_KERNELS_CUH

@@ -14,6 +14,7 @@
 
 #include "bbfft/cuda/online_compiler.hpp"
 
+#include <cstdlib>
 #include <dirent.h>
 #include <dlfcn.h>
 
@@ -275,25 +276,137 @@ void nd_passes(configuration const &cfg, std::function<void(configuration const 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fused 2d
+// ------------------------------------------------------------------------------------------
+fft2d_plan::fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::string const &tune)
+    : api_(std::move(a)) {
+    K_ = prob.K;
+    tp_ = plan_kernel_2d(prob, api_.props(), tune);
+    slice_bytes_ = std::size_t(tp_.p.tile_stride) * 2 * std::size_t(prob.fp);
+    jit_cache_key key{tp_.identifier, api_.device_id()};
+    if (cache) module_ = cache->get(key);
+    if (!module_) module_ = builtin_module(tp_.identifier, api_.device());
+    if (!module_) {
+        module_ = api_.build_module(tp_.source);
+        if (cache) cache->store(key, module_);
+    }
+    kernel_ = api_.create_kernel(module_.get(), tp_.identifier, tp_.p.smem_bytes);
+    twiddle_ = api_.create_twiddle_table(tp_.twiddle, tp_.p.fp);
+}
+
+fft2d_plan::~fft2d_plan() { api_.release_buffer(twiddle_); }
+
+void fft2d_plan::enqueue(void const *in, void *out, cudaStream_t stream) { enqueue_slab(in, out, 0, K_, stream); }
+
+void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
+                              cudaStream_t stream) {
+    if (k0 + count > K_) throw bad_configuration("slab exceeds the planned batch");
+    if (count == 0) return;
+    kernel_args a = {};
+    a.in = static_cast<char const *>(in) + k0 * slice_bytes_;
+    a.out = static_cast<char *>(out) + k0 * slice_bytes_;
+    a.tw = twiddle_;
+    a.K = count;
+    a.M = tp_.p.M;
+    api_.launch_kernel(kernel_, count, tp_.p.threads, tp_.p.smem_bytes, a, stream);
+}
+
+// Steps of a 2d/3d plan.  c2c transforms in the default layout whose M x N1 x N2 tile fits into
+// shared memory run modes 1 and 2 fused (BBFFT_CUDA_ND_FUSE=0 turns this off: "multi-pass").
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev) {
+    std::vector<nd_step> steps;
+    const std::uint64_t K = cfg.shape[cfg.dim + 1];
+    std::vector<configuration> passes;
+    nd_passes(cfg, [&](configuration const &c) { passes.push_back(c); }); // validates the layout, too
+    char const *fuse_env = std::getenv("BBFFT_CUDA_ND_FUSE");
+    bool fuse = !(fuse_env && *fuse_env == '0') && cfg.type == transform_type::c2c && cfg.dim >= 2;
+    problem_2d t;
+    if (fuse) {
+        t.fp = static_cast<int>(cfg.fp);
+        t.dir = static_cast<int>(cfg.dir);
+        t.M = cfg.shape[0];
+        t.N1 = cfg.shape[1];
+        t.N2 = cfg.shape[2];
+        t.K = (cfg.dim == 3 ? cfg.shape[3] : 1) * K;
+        t.tile_stride = t.M * t.N1 * t.N2;
+        fuse = tile_fusable(t, dev);
+    }
+    std::size_t first = 0;
+    if (fuse) {
+        nd_step s;
+        s.fused = true;
+        s.tile = t;
+        s.mult = K ? t.K / K : 0;
+        steps.push_back(s);
+        first = 2;
+    }
+    for (std::size_t d = first; d < passes.size(); ++d) {
+        nd_step s;
+        s.pass = passes[d];
+        s.mult = K ? passes[d].shape[2] / K : 0;
+        steps.push_back(s);
+    }
+    return steps;
+}
+
 nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::move(a)), dim_(cfg.dim) {
-    nd_passes(cfg, [&](configuration const &c) {
-        plans_.push_back(std::make_shared<fft1d_plan>(c, api_, cache));
-    });
+    K_ = cfg.shape[dim_ + 1];
+    for (auto const &s : nd_decompose(cfg, api_.props())) {
+        if (s.fused) {
+            plans_.push_back(std::make_shared<fft2d_plan>(s.tile, api_, cache));
+        } else {
+            plans_.push_back(std::make_shared<fft1d_plan>(s.pass, api_, cache));
+        }
+        // step d sees mult_[d] slices per outer k
+        mult_.push_back(s.mult);
+    }
     std::size_t real_bytes = static_cast<std::size_t>(cfg.fp);
     std::size_t ibytes = (cfg.type == transform_type::r2c ? 1 : 2) * real_bytes;
     std::size_t obytes = (cfg.type == transform_type::c2r ? 1 : 2) * real_bytes;
     std::size_t isize = cfg.istride[dim_ + 1] * cfg.shape[dim_ + 1] * ibytes;
     std::size_t osize = cfg.ostride[dim_ + 1] * cfg.shape[dim_ + 1] * obytes;
     if (isize > osize) tmp_ = api_.create_device_buffer(isize);
+
+    // L2 blocking: run all passes over one block of outer k before moving to the next, with the
+    // block sized to stay resident in the 126 MB L2.  Passes 2..d then read what the previous pass
+    // just wrote from L2 and overwrite it in place, so HBM sees roughly one read of the input and
+    // one write of the output instead of one round trip per pass (reference nd_fft.hpp:140-152
+    // runs every pass over the whole tensor).  BBFFT_CUDA_ND_BLOCK_BYTES overrides; 0 disables.
+    std::size_t block_bytes = std::size_t(24) << 20;
+    if (char const *e = std::getenv("BBFFT_CUDA_ND_BLOCK_BYTES")) block_bytes = std::strtoull(e, nullptr, 10);
+    std::size_t per_k = std::max(cfg.istride[dim_ + 1] * ibytes, cfg.ostride[dim_ + 1] * obytes);
+    kblock_ = K_;
+    if (block_bytes > 0 && per_k > 0 && K_ > 1) {
+        kblock_ = std::max<std::uint64_t>(1, block_bytes / per_k);
+        // odd-N real transforms pair the slices (2k', 2k'+1) of their pass: keep blocks even
+        if (cfg.type != transform_type::c2c && cfg.shape[1] % 2 == 1 && kblock_ % 2 == 1) ++kblock_;
+        if (kblock_ >= K_) kblock_ = K_;
+    }
 }
 
 nd_plan::~nd_plan() { api_.release_buffer(tmp_); }
 
+unsigned nd_plan::launches_per_execute() const {
+    std::uint64_t blocks = kblock_ ? (K_ + kblock_ - 1) / kblock_ : 1;
+    return unsigned(plans_.size() * std::max<std::uint64_t>(1, blocks));
+}
+
 void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
     void *tmp = tmp_ ? tmp_ : out;
-    plans_[0]->enqueue(in, tmp, stream);
-    for (unsigned d = 1; d + 1 < dim_; ++d) plans_[d]->enqueue(tmp, tmp, stream);
-    plans_[dim_ - 1]->enqueue(tmp, out, stream);
+    const std::size_t n = plans_.size();
+    auto src = [&](std::size_t d) { return d == 0 ? in : static_cast<void const *>(tmp); };
+    auto dst = [&](std::size_t d) { return d + 1 == n ? out : tmp; };
+    if (kblock_ == 0 || kblock_ >= K_) {
+        for (std::size_t d = 0; d < n; ++d) plans_[d]->enqueue(src(d), dst(d), stream);
+        return;
+    }
+    for (std::uint64_t k0 = 0; k0 < K_; k0 += kblock_) {
+        const std::uint64_t cnt = std::min<std::uint64_t>(kblock_, K_ - k0);
+        for (std::size_t d = 0; d < n; ++d) {
+            plans_[d]->enqueue_slab(src(d), dst(d), k0 * mult_[d], cnt * mult_[d], stream);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -341,7 +454,19 @@ std::vector<std::string> generate_fft_kernels(std::ostream &os, std::vector<conf
             emit(cfg);
         } else {
             // same decomposition as nd_plan, without a device
-            cuda::nd_passes(cfg, emit);
+            for (auto const &st : cuda::nd_decompose(cfg, dev)) {
+                if (!st.fused) {
+                    emit(st.pass);
+                    continue;
+                }
+                auto tp = cuda::plan_kernel_2d(st.tile, dev, std::string());
+                bool seen = false;
+                for (auto const &n : names) seen = seen || n == tp.identifier;
+                if (!seen) {
+                    names.push_back(tp.identifier);
+                    os << tp.source << "\n";
+                }
+            }
         }
     }
     return names;

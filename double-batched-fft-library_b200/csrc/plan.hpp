@@ -35,6 +35,8 @@ class plan_base : public detail::plan_impl<event> {
     virtual void enqueue_slab(void const *, void *, std::uint64_t, std::uint64_t, cudaStream_t) {
         throw bad_configuration("plan cannot be sliced");
     }
+    // identifiers of the kernels this plan launches (cache keys)
+    virtual void kernel_names(std::vector<std::string> &names) const = 0;
     auto execute(void const *in, void *out, std::vector<event> const &dep_events) -> event override;
 };
 
@@ -49,6 +51,7 @@ class fft1d_plan : public plan_base {
     cudaStream_t stream() const override { return api_.stream(); }
     unsigned launches_per_execute() const override { return 1; }
     kernel_plan const &kernel() const { return kp_; }
+    void kernel_names(std::vector<std::string> &names) const override { names.push_back(kp_.identifier); }
     std::uint64_t slices() const override { return K_; }
     std::size_t in_slice_bytes() const override { return in_slice_bytes_; }
     std::size_t out_slice_bytes() const override { return out_slice_bytes_; }
@@ -65,6 +68,46 @@ class fft1d_plan : public plan_base {
     void *twiddle_ = nullptr;
 };
 
+// Fused 2d c2c plan: one launch of bbk::fft2d_tile, one CTA per M x N1 x N2 tile held in shared
+// memory (replaces two chained 1d passes of the reference's nd_fft when the tile fits).
+class fft2d_plan : public plan_base {
+  public:
+    fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::string const &tune = std::string());
+    ~fft2d_plan() override;
+    fft2d_plan(fft2d_plan const &) = delete;
+    fft2d_plan &operator=(fft2d_plan const &) = delete;
+
+    void enqueue(void const *in, void *out, cudaStream_t stream) override;
+    cudaStream_t stream() const override { return api_.stream(); }
+    unsigned launches_per_execute() const override { return 1; }
+    tile_plan const &kernel() const { return tp_; }
+    void kernel_names(std::vector<std::string> &names) const override { names.push_back(tp_.identifier); }
+    std::uint64_t slices() const override { return K_; }
+    std::size_t in_slice_bytes() const override { return slice_bytes_; }
+    std::size_t out_slice_bytes() const override { return slice_bytes_; }
+    void enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
+                      cudaStream_t stream) override;
+
+  private:
+    api api_;
+    tile_plan tp_;
+    std::uint64_t K_ = 0;
+    std::size_t slice_bytes_ = 0;
+    shared_handle<module_handle_t> module_;
+    cudaKernel_t kernel_ = nullptr;
+    void *twiddle_ = nullptr;
+};
+
+// One step of a 2d/3d decomposition: either a fused tile launch over dims (1,2) or a
+// double-batched 1d pass; `mult` = slices of the step per outer k.
+struct nd_step {
+    bool fused = false;
+    problem_2d tile;
+    configuration pass;
+    std::uint64_t mult = 1;
+};
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev);
+
 class nd_plan : public plan_base {
   public:
     nd_plan(configuration const &cfg, api a, jit_cache *cache);
@@ -74,13 +117,19 @@ class nd_plan : public plan_base {
 
     void enqueue(void const *in, void *out, cudaStream_t stream) override;
     cudaStream_t stream() const override { return api_.stream(); }
-    unsigned launches_per_execute() const override { return dim_; }
-    std::vector<std::shared_ptr<fft1d_plan>> const &passes() const { return plans_; }
+    unsigned launches_per_execute() const override;
+    std::vector<std::shared_ptr<plan_base>> const &passes() const { return plans_; }
+    void kernel_names(std::vector<std::string> &names) const override {
+        for (auto const &q : plans_) q->kernel_names(names);
+    }
+    std::uint64_t k_block() const { return kblock_; }
 
   private:
     api api_;
     unsigned dim_;
-    std::vector<std::shared_ptr<fft1d_plan>> plans_;
+    std::vector<std::shared_ptr<plan_base>> plans_;
+    std::vector<std::uint64_t> mult_; // slices of pass d per outer k
+    std::uint64_t K_ = 0, kblock_ = 0; // outer batch and its L2 block (in k)
     void *tmp_ = nullptr;
 };
 

@@ -13,6 +13,9 @@
 
 namespace bbfft::cuda {
 
+static void unit_root(long num, long den, int dir, double &re, double &im);
+static void emit_w_table(std::ostringstream &os, int R);
+
 // ------------------------------------------------------------------------------------------
 // integer helpers
 // ------------------------------------------------------------------------------------------
@@ -389,14 +392,19 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     }
     auto tune = parse_tune(tune_str);
     {
-        // measured wisdom applies to complex transforms whose batch rows fill the wisdom's lanes;
-        // explicit overrides win.  BBFFT_CUDA_NO_WISDOM=1 turns it off (used by the tuner).
+        // Measured wisdom (c2c sweep) applies when the batch rows fill the wisdom's lanes.  Real
+        // transforms run the same stages on their complex length (N/2 for even N), so they take
+        // the entry of that length as their starting point.  Explicit overrides win;
+        // BBFFT_CUDA_NO_WISDOM=1 turns it off (used by the tuner).
         char const *off = std::getenv("BBFFT_CUDA_NO_WISDOM");
-        char const *w = (prob.type == 0 && !(off && *off == '1')) ? wisdom_lookup(prob.fp, int(prob.N)) : nullptr;
+        const std::uint64_t clen = (prob.type != 0 && prob.N % 2 == 0) ? prob.N / 2 : prob.N;
+        char const *w = !(off && *off == '1') ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
         if (w && *w) {
             auto wt = parse_tune(w);
             int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;
-            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
+            // real in-place transforms need all m of a k slice in one CTA (see inplace_unsupported)
+            const bool covers = prob.type == 0 || std::uint64_t(wml) >= prob.M;
+            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0 && covers) {
                 for (auto const &kv : wt) {
                     if (!tune.count(kv.first)) tune[kv.first] = kv.second;
                 }
@@ -829,6 +837,279 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
        << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
     os << "#ifdef BBFFT_OCL_COMPAT\n#undef float2\n#undef double2\n#undef BBFFT_OCL_COMPAT\n#endif\n";
     return os.str();
+}
+
+// ------------------------------------------------------------------------------------------
+// fused 2d tile kernel
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// fewest stages with radices <= rmax (a prime factor above rmax is its own radix), then the
+// cheapest butterflies, then the most balanced split
+std::vector<int> tile_radices(int N, int rmax) {
+    std::vector<std::vector<int>> facs;
+    std::vector<int> cur;
+    enum_factorizations(N, std::max(rmax, max_prime(N)), 4, cur, facs);
+    std::vector<int> best;
+    double best_cost = 1e30;
+    for (auto const &f : facs) {
+        double cost = 100.0 * f.size();
+        int mx = 0;
+        for (int r : f) {
+            cost += radix_cost(r) * 0.1;
+            mx = std::max(mx, r);
+        }
+        cost += 0.01 * mx;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = f;
+        }
+    }
+    if (best.empty()) throw std::runtime_error("bbfft-cuda planner: no tile factorization for N=" + std::to_string(N));
+    return best;
+}
+
+int tile_regs_complex(tile_params const &p) {
+    int regs = 0;
+    for (tile_pass_params const *q : {&p.a, &p.b}) {
+        for (int s = 0; s < q->L; ++s) {
+            long total = long(q->S) * (q->N / q->radix[s]) * q->O;
+            int cnt = int((total + p.threads - 1) / p.threads);
+            regs = std::max(regs, cnt * q->radix[s]);
+        }
+    }
+    return regs;
+}
+
+int tile_phys(int lin, int padk) { return padk > 0 ? lin + lin / padk : lin; }
+
+int pass_bin_of_sub(tile_pass_params const &q, int u) {
+    int digits[4] = {0, 0, 0, 0};
+    int rem = u;
+    for (int s = q.L - 2; s >= 0; --s) {
+        digits[s] = rem % q.radix[s];
+        rem /= q.radix[s];
+    }
+    int k = 0;
+    for (int s = q.L - 2; s >= 0; --s) k = k * q.radix[s] + digits[s];
+    return k;
+}
+
+// excess shared-memory wavefronts of warps 0 and 1 over every smem phase of the tile kernel
+long tile_layout_score(tile_params const &p, int padk) {
+    const int elem_bytes = 2 * p.fp;
+    kernel_params dummy;
+    layout_eval ev{dummy, elem_bytes};
+    long excess = 0;
+    int pass_no = 0;
+    for (tile_pass_params const *q : {&p.a, &p.b}) {
+        for (int s = 0; s < q->L; ++s) {
+            const int R = q->radix[s];
+            int NS = q->N;
+            for (int i = 0; i < s; ++i) NS /= q->radix[i];
+            const int NS1 = NS / R, NSUB = q->N / R;
+            const long total = long(q->S) * NSUB * q->O;
+            const int cnt = int((total + p.threads - 1) / p.threads);
+            const bool last = s == q->L - 1;
+            const bool reads = !(pass_no == 0 && s == 0);
+            const bool writes_inplace = !last;
+            const bool writes_sorted = last && pass_no == 0;
+            for (int warp = 0; warp < std::min(2, (p.threads + 31) / 32); ++warp) {
+                for (int i = 0; i < std::min(cnt, 2); ++i) {
+                    for (int j = 0; j < R; ++j) {
+                        std::vector<int> inpl(32, -1), sorted(32, -1);
+                        for (int l = 0; l < 32; ++l) {
+                            long id = long(warp) * 32 + l + long(p.threads) * i;
+                            if (id >= total) continue;
+                            int lo = int(id % q->S);
+                            long r = id / q->S;
+                            int u = int(r % NSUB), hi = int(r / NSUB);
+                            int base = lo + q->S * ((u / NS1) * NS + u % NS1) + q->S * q->N * hi;
+                            inpl[l] = tile_phys(base + q->S * NS1 * j, padk);
+                            if (last) {
+                                int b2 = lo + q->S * pass_bin_of_sub(*q, u) + q->S * q->N * hi;
+                                sorted[l] = tile_phys(b2 + q->S * (q->N / R) * j, padk);
+                            }
+                        }
+                        int e = ev.wavefronts(inpl) - ev.ideal(inpl);
+                        excess += e * ((reads ? 1 : 0) + (writes_inplace ? 1 : 0));
+                        if (writes_sorted) excess += ev.wavefronts(sorted) - ev.ideal(sorted);
+                    }
+                }
+            }
+        }
+        ++pass_no;
+    }
+    return excess;
+}
+
+std::size_t tile_smem_bytes(std::uint64_t tile, int padk, int fp) {
+    return std::size_t(tile_phys(int(tile - 1), padk) + 1) * 2 * fp;
+}
+
+} // namespace
+
+bool tile_fusable(problem_2d const &prob, device_props const &dev) {
+    if (prob.N1 < 2 || prob.N2 < 2) return false;
+    const std::uint64_t tile = prob.M * prob.N1 * prob.N2;
+    if (tile < 1024 || tile > (1u << 20)) return false;
+    // padding candidates that would not fit are skipped by the layout search
+    if (tile_smem_bytes(tile, 0, prob.fp) > std::min<std::size_t>(dev.max_smem_per_block, 200 * 1024)) return false;
+    int big = std::max(max_prime(int(prob.N1)), max_prime(int(prob.N2)));
+    return big <= 31;
+}
+
+tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::string const &tune_str) {
+    auto tune = parse_tune(tune_str);
+    tile_plan plan;
+    tile_params &p = plan.p;
+    p.fp = prob.fp;
+    p.dir = prob.dir;
+    p.M = prob.M;
+    p.N1 = prob.N1;
+    p.N2 = prob.N2;
+    const std::uint64_t tile = prob.M * prob.N1 * prob.N2;
+    p.tile_stride = prob.tile_stride ? prob.tile_stride : tile;
+    const int rmax = 16;
+    auto ra = tune.count("RA") ? parse_radices(tune["RA"]) : tile_radices(int(prob.N1), rmax);
+    auto rb = tune.count("RB") ? parse_radices(tune["RB"]) : tile_radices(int(prob.N2), rmax);
+    auto fill = [](tile_pass_params &q, std::vector<int> const &r, int N, int S, int O) {
+        int prod = 1;
+        for (int x : r) prod *= x;
+        if (prod != N || r.size() > 4 || r.empty()) {
+            throw std::runtime_error("bbfft-cuda planner: tile radices do not multiply to N");
+        }
+        q.N = N;
+        q.S = S;
+        q.O = O;
+        q.L = int(r.size());
+        for (int s = 0; s < 4; ++s) q.radix[s] = s < q.L ? r[s] : 1;
+    };
+    fill(p.a, ra, int(prob.N1), int(prob.M), int(prob.N2));
+    fill(p.b, rb, int(prob.N2), int(prob.M * prob.N1), 1);
+
+    // threads: ~16 (fp32) / ~8-16 (fp64) complex elements per thread
+    if (tune.count("TH")) {
+        p.threads = std::atoi(tune["TH"].c_str());
+    } else {
+        const std::uint64_t ept = 16;
+        int th = 64;
+        while (th < dev.max_threads_per_block && std::uint64_t(th) * ept < tile) th *= 2;
+        p.threads = th;
+    }
+    if (p.threads < 32 || p.threads > dev.max_threads_per_block || p.threads % 32) {
+        throw std::runtime_error("bbfft-cuda planner: bad tile CTA size");
+    }
+    // padding
+    {
+        long best = -1;
+        int best_padk = 0;
+        for (int padk : {0, 64, 32, 16, 8}) {
+            if (tile_smem_bytes(tile, padk, p.fp) > dev.max_smem_per_block) continue;
+            long sc = tile_layout_score(p, padk) * 64 + (padk ? 64 / padk : 0);
+            if (best < 0 || sc < best) {
+                best = sc;
+                best_padk = padk;
+            }
+        }
+        p.PADK = best_padk;
+    }
+    if (tune.count("PADK")) p.PADK = std::atoi(tune["PADK"].c_str());
+    p.smem_bytes = tile_smem_bytes(tile, p.PADK, p.fp);
+    if (p.smem_bytes > dev.max_smem_per_block) {
+        throw std::runtime_error("bbfft-cuda planner: tile does not fit into shared memory");
+    }
+    // resident CTAs
+    {
+        int words = (p.fp == 4 ? 2 : 4) * tile_regs_complex(p);
+        int need = words + words / 4 + 32;
+        int mb = int(std::min<std::size_t>({std::size_t(4), dev.smem_per_sm / (p.smem_bytes + 1024),
+                                            std::size_t(2048 / p.threads)}));
+        mb = std::max(mb, 1);
+        while (mb > 1 && reg_cap(p.threads, mb) < need) --mb;
+        p.min_blocks = mb;
+    }
+    if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
+    p.max_regs = reg_cap(p.threads, p.min_blocks);
+
+    // identifier
+    {
+        std::ostringstream os;
+        os << "bbfft_c2c2d" << (p.dir < 0 ? "_m1" : "_p1") << "_f" << (p.fp * 8) << "_M" << p.M << "_N" << p.N1
+           << "x" << p.N2 << "_ra";
+        for (int s = 0; s < p.a.L; ++s) os << (s ? "x" : "") << p.a.radix[s];
+        os << "_rb";
+        for (int s = 0; s < p.b.L; ++s) os << (s ? "x" : "") << p.b.radix[s];
+        os << "_th" << p.threads << "_mb" << p.min_blocks << "_pk" << p.PADK << "_ts" << p.tile_stride;
+        plan.identifier = os.str();
+    }
+    // twiddles: pass A stages, then pass B stages (same construction as the 1d table)
+    std::vector<int> off_a(4, 0), off_b(4, 0);
+    {
+        auto add = [&](tile_pass_params const &q, std::vector<int> &off) {
+            int NS = q.N;
+            for (int s = 0; s < q.L; ++s) {
+                off[s] = int(plan.twiddle.size() / 2);
+                int R = q.radix[s], NS1 = NS / R;
+                if (s + 1 < q.L) {
+                    for (int qq = 1; qq < R; ++qq) {
+                        for (int n2 = 0; n2 < NS1; ++n2) {
+                            double re, im;
+                            unit_root(long(n2) * qq, NS, p.dir, re, im);
+                            plan.twiddle.push_back(re);
+                            plan.twiddle.push_back(im);
+                        }
+                    }
+                }
+                NS = NS1;
+            }
+        };
+        add(p.a, off_a);
+        add(p.b, off_b);
+        if (plan.twiddle.empty()) {
+            plan.twiddle.push_back(1.0);
+            plan.twiddle.push_back(0.0);
+        }
+    }
+    // stub
+    {
+        std::ostringstream os;
+        const char *real = p.fp == 4 ? "float" : "double";
+        os << "// generated by bbfft-cuda planner -- do not edit\n#include \"bbfft_kernels.cuh\"\n";
+        os << "namespace stub_" << plan.identifier << " {\n";
+        std::set<int> rs;
+        for (int s = 0; s < p.a.L; ++s) rs.insert(p.a.radix[s]);
+        for (int s = 0; s < p.b.L; ++s) rs.insert(p.b.radix[s]);
+        for (int r : rs) emit_w_table(os, r);
+        auto emit_pass = [&](char const *name, tile_pass_params const &q, std::vector<int> const &off) {
+            os << "struct " << name << " {\n    static constexpr int N = " << q.N << ", S = " << q.S << ", O = " << q.O
+               << ", L = " << q.L << ";\n";
+            os << "    static BBK_CE int radix(int s) {\n        constexpr int r[4] = {" << q.radix[0] << ", "
+               << q.radix[1] << ", " << q.radix[2] << ", " << q.radix[3] << "};\n        return r[s];\n    }\n";
+            os << "    static BBK_CE int tw_off(int s) {\n        constexpr int r[4] = {" << off[0] << ", " << off[1]
+               << ", " << off[2] << ", " << off[3] << "};\n        return r[s];\n    }\n";
+            os << "    template <int S_, int Dummy = 0> struct WRsel;\n";
+            for (int s = 0; s < q.L; ++s) {
+                os << "    template <int Dummy> struct WRsel<" << s << ", Dummy> { using type = W" << q.radix[s]
+                   << "; };\n";
+            }
+            os << "    template <int S_> using WR = typename WRsel<S_>::type;\n};\n";
+        };
+        emit_pass("PassA", p.a, off_a);
+        emit_pass("PassB", p.b, off_b);
+        os << "struct C {\n    using real_t = " << real << ";\n    using PA = PassA;\n    using PB = PassB;\n";
+        os << "    static constexpr int DIR = " << p.dir << ", THREADS = " << p.threads << ", PADK = " << p.PADK
+           << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull;\n";
+        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
+              "        return reinterpret_cast<const bbk::cx<real_t> *>(in)[off];\n    }\n";
+        os << "    static BBK_DEV void st(void *out, bbk::u64 off, bbk::cx<real_t> v) {\n"
+              "        reinterpret_cast<bbk::cx<real_t> *>(out)[off] = v;\n    }\n";
+        os << "};\n} // namespace stub_" << plan.identifier << "\n";
+        os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") " << plan.identifier
+           << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
+        plan.source = os.str();
+    }
+    return plan;
 }
 
 } // namespace bbfft::cuda

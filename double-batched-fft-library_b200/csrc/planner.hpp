@@ -82,6 +82,39 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
 std::string make_identifier(kernel_params const &p);
 std::vector<double> make_twiddles(kernel_params const &p);
 
+// ---- fused 2d tile kernel (bbk::fft2d_tile): c2c, default packed layout, one CTA per tile ----
+struct problem_2d {
+    int fp = 4, dir = -1;
+    std::uint64_t M = 1, N1 = 1, N2 = 1, K = 1; // K = number of tiles
+    std::uint64_t tile_stride = 0;              // elements between consecutive tiles (0 = packed)
+};
+
+struct tile_pass_params {
+    int N = 1, S = 1, O = 1, L = 1;
+    int radix[4] = {1, 1, 1, 1};
+};
+
+struct tile_params {
+    int fp = 4, dir = -1;
+    std::uint64_t M = 1, N1 = 1, N2 = 1, tile_stride = 0;
+    tile_pass_params a, b; // axis n1, axis n2
+    int threads = 256, PADK = 0, min_blocks = 1, max_regs = 255;
+    std::size_t smem_bytes = 0;
+};
+
+struct tile_plan {
+    tile_params p;
+    std::string identifier, source;
+    std::vector<double> twiddle;
+};
+
+// True when the M x N1 x N2 tile (plus padding) fits the shared memory of one CTA and is large
+// enough to be worth a CTA of its own.
+bool tile_fusable(problem_2d const &prob, device_props const &dev);
+// Tuning overrides: RA=8x16, RB=16x8, TH=<threads>, PADK, MB.
+tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev,
+                         std::string const &tune = std::string());
+
 // integer helpers (pinned by tests; semantics of reference src/base/prime_factorization.cpp)
 std::vector<int> prime_factors(int n);
 bool radix_supported(int r);

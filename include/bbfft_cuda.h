@@ -80,6 +80,8 @@ int bbfft_cuda_plan_destroy(bbfft_cuda_plan_t plan);
 /* Introspection: kernels launched per execute and their identifiers (cache keys,
  * reference: src/base/generator/small_batch_fft.cpp:60-80). */
 int bbfft_cuda_plan_num_kernels(bbfft_cuda_plan_t plan);
+/* kernel launches issued by one execute (2d/3d plans run their passes once per L2 block of k) */
+int bbfft_cuda_plan_launches(bbfft_cuda_plan_t plan);
 const char *bbfft_cuda_plan_kernel_name(bbfft_cuda_plan_t plan, int index);
 
 /* Device-free planning and code generation (bbfft::generate_fft_kernels,

@@ -49,14 +49,16 @@ def _compile(desc):
 
 
 def run(cfg, inp, out=None, tune=""):
-    """Execute the planned kernel for 1d `cfg` on numpy buffers (out=None -> in place)."""
+    """Execute the planned kernel for a 1d (or fused 2d) `cfg` on numpy buffers (out=None -> in place)."""
     desc = pkg.describe(cfg, tune)
     lib = _compile(desc)
     lib.emu_launch.argtypes = [C.POINTER(Args), C.c_ulonglong, C.c_int, C.c_ulong]
     tw = desc["twiddle"].astype(np.float32 if desc["fp"] == 4 else np.float64)
     if out is None:
         out = inp
-    a = Args(inp.ctypes.data, out.ctypes.data, tw.ctypes.data, cfg.shape[2], cfg.shape[0], cfg.istride[1],
+    # 1d: K slices; fused 2d: the kernel's K argument counts tiles (= CTAs)
+    nk = cfg.shape[2] if cfg.dim == 1 else desc["grid"]
+    a = Args(inp.ctypes.data, out.ctypes.data, tw.ctypes.data, nk, cfg.shape[0], cfg.istride[1],
              cfg.istride[2], cfg.ostride[1], cfg.ostride[2])
     rc = lib.emu_launch(C.byref(a), desc["grid"], desc["threads"], desc["smem_bytes"])
     if rc != 0:

@@ -29,7 +29,10 @@ def test_c2c_nd(pkg, fp, M, Ns, K):
     for d, inplace in ((pkg.FORWARD, False), (pkg.BACKWARD, True)):
         cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, d, pkg.C2C, inplace=inplace)
         plan = pkg.Plan(cfg, stream=_stream())
-        assert plan.launches_per_execute == dim
+        # modes 1 and 2 run fused in one launch when their tile fits into shared memory
+        fused = plan.kernel_names[0].startswith("bbfft_c2c2d")
+        assert len(plan.kernel_names) == (dim - 1 if fused else dim)
+        assert fused == (M * Ns[0] * Ns[1] >= 1024)
         xd = torch.from_numpy(x).cuda()
         if inplace:
             plan.execute(xd)
@@ -104,3 +107,42 @@ def test_nd_rejects_custom_strides(pkg):
     cfg = pkg.make_config(2, [2, 8, 8, 2], 4, pkg.FORWARD, pkg.C2C, istride=[1, 3, 24, 200], ostride=[1, 3, 24, 200])
     with pytest.raises(pkg.BadConfiguration):
         pkg.Plan(cfg, stream=_stream())
+
+
+@pytest.mark.parametrize("fp,M,Ns,K", [(4, 1, (128, 128), 5), (8, 1, (64, 64, 64), 3), (4, 2, (32, 48), 7),
+                                       (8, 1, (30, 36, 20), 4), (4, 16, (8, 8, 8), 6)])
+def test_c2c_nd_fused_equals_multipass_and_l2_blocking(pkg, monkeypatch, fp, M, Ns, K):
+    """BASELINE config 4 shapes: the shared-memory-fused plan, the multi-pass plan
+    (BBFFT_CUDA_ND_FUSE=0, the reference's nd_fft decomposition) and L2-blocked execution
+    (several k blocks per execute) agree with each other and with numpy."""
+    dim = len(Ns)
+    rng = np.random.default_rng(17 + sum(Ns))
+    shape_np = (K,) + tuple(reversed(Ns)) + (M,)
+    x = (rng.standard_normal(shape_np) + 1j * rng.standard_normal(shape_np)).astype(cdtype(fp))
+    ref = np.fft.fftn(x.astype(np.complex128), axes=_axes(dim))
+    xd = torch.from_numpy(x).cuda()
+    per_k = x.nbytes // K
+    results = {}
+    for name, env in (("fused", {}), ("multipass", {"BBFFT_CUDA_ND_FUSE": "0"}),
+                      ("fused-blocked", {"BBFFT_CUDA_ND_BLOCK_BYTES": str(2 * per_k)}),
+                      ("multipass-unblocked", {"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_BLOCK_BYTES": "0"})):
+        for k in ("BBFFT_CUDA_ND_FUSE", "BBFFT_CUDA_ND_BLOCK_BYTES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, pkg.FORWARD, pkg.C2C, inplace=False)
+        plan = pkg.Plan(cfg, stream=_stream())
+        yd = torch.zeros_like(xd)
+        plan.execute(xd, yd)
+        torch.cuda.synchronize()
+        results[name] = (yd.cpu().numpy(), plan.kernel_names, plan.launches_per_execute)
+        plan.close()
+    assert results["fused"][1][0].startswith("bbfft_c2c2d")
+    assert not results["multipass"][1][0].startswith("bbfft_c2c2d")
+    assert len(results["multipass"][1]) == dim and results["multipass-unblocked"][2] == dim
+    assert results["fused-blocked"][2] == (dim - 1) * ((K + 1) // 2)
+    for name, (y, names, _) in results.items():
+        assert rel_l2(y, ref) < TOL[fp], (name, names)
+    # blocking only changes the launch schedule, never the arithmetic
+    assert np.array_equal(results["fused"][0], results["fused-blocked"][0])
+    assert np.array_equal(results["multipass"][0], results["multipass-unblocked"][0])

@@ -20,9 +20,12 @@ def real_occupancy(reg, threads, smem):
     return min(by_reg, by_smem, 2048 // threads, 32), min(by_reg_cons, by_smem, 2048 // threads, 32)
 
 
-def one(desc):
+def one(desc, tune=""):
     cfg = pkg.parse_descriptor(desc)
-    d = pkg.describe(cfg, "")
+    try:
+        d = pkg.describe(cfg, tune)
+    except pkg.BadConfiguration:
+        return desc, None  # multi-kernel (nd) plan
     cubin = pkg.compile_to_cubin(d["source"])
     with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
         f.write(cubin); f.flush()
@@ -37,7 +40,7 @@ def one(desc):
 if __name__ == "__main__":
     descs = [d for d in aot.BUILTIN_DESCRIPTORS]
     with ThreadPoolExecutor(8) as ex:
-        res = dict(ex.map(one, descs))
+        res = {k: v for k, v in ex.map(one, descs) if v is not None}
     json.dump(res, open(sys.argv[1], "w"), indent=1)
     for k, v in res.items():
         mb = int(re.search(r"_mb(\d+)_", v["id"]).group(1))
