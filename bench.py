@@ -31,6 +31,10 @@ PKG = "double-batched-fft-library_b200"
 
 M_BATCH = 16
 TENSOR_BYTES = 1 << 30
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch (2 GiB = 2147483648 algorithmic bytes)
+# from the ncu --set full capture of the N=64 fp32 kernel of this sweep
+NCU_TRAFFIC_PER_LAUNCH = 1073814000 + 1022701000
+NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_summary.txt (c2c f32 M=16 N=64: read 1.0738 GB + write 1.0227 GB; the tail of the output is still dirty in L2 when the kernel ends)"
 
 
 def sweep_sizes():
@@ -210,6 +214,37 @@ def measure_e2e(args, torch, dist, plans, world, dev, barrier, total_flops):
             "api": "bbfft_cuda_plan_execute_host: pinned host buffers, H2D + kernel + D2H per plan, pipelined over k slabs"}
 
 
+def other_configs(peak):
+    """BASELINE.json configs 1, 3, 4, 5 (single launches, outside the timed region of the headline
+    sweep): algorithmic GB/s, fraction of the measured HBM peak, cuFFT (torch.fft) on the same
+    tensors.  Measured by tools/bench_configs.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import contextlib
+    import io
+    import torch
+    import bench_configs as bc
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        bc.bench_c2c_1d(rows, "C1 1d c2c f32 N=64 M=1 K=16384 (L2 resident)", 4, 1, 64, 16384, stream)
+        bc.bench_c2c_1d(rows, "C1 shape at 1 GiB", 4, 1, 64, (1 << 30) // (64 * 8), stream)
+        for ttype, nm in ((bc.pkg.R2C, "C3 r2c f32 N=256 K=2^20"), (bc.pkg.C2R, "C3 c2r f32 N=256 K=2^20")):
+            for inplace in (False, True):
+                bc.bench_real_1d(rows, nm, 4, 1, 256, 1 << 20, stream, ttype, inplace)
+        bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64", 8, (64, 64, 64), 64, stream)
+        bc.bench_nd(rows, "C4 2d c2c f32 128^2 K=64 (L2 resident)", 4, (128, 128), 64, stream)
+        bc.bench_nd(rows, "C4 2d shape at 1 GiB", 4, (128, 128), 8192, stream)
+        bc.bench_c2c_1d(rows, "C5 c2c f32 M=16 N=256 identity load/store callbacks", 4, 16, 256, (1 << 30) // (16 * 256 * 8),
+                        stream, callbacks=(bc.IDENTITY_CB % dict(v="float2"), "load", "store", "cuda"))
+    out = []
+    for r in rows:
+        out.append({"config": r["config"] + (" " + r["note"] if r["note"] else ""), "GBs": round(r["GBs"], 1),
+                    "frac_of_peak": round(r["GBs"] / peak, 4), "GFLOPs": round(r["GFLOPs"], 1),
+                    "time_us": round(r["time_us"], 2), "cufft_GBs": round(r["cufft_GBs"], 1) if r["cufft_GBs"] else None,
+                    "rel_l2_vs_fp64": r["err"], "launches": r["launches"]})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
@@ -222,6 +257,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--per-size", default="", help="write the per-size table to this CSV")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (C1, C3, C4, C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -322,7 +358,8 @@ def main():
     bytes_rank = total_bytes / world
     roofline = {
         "bound": "hbm", "achieved": bytes_rank / kernel_time * 1e-9, "peak": peak, "unit": "GB/s",
-        "frac": bytes_rank / kernel_time * 1e-9 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": bytes_rank / kernel_time * 1e-9 / peak, "traffic": NCU_TRAFFIC_PER_LAUNCH, "peak_source": peak_src,
+        "traffic_source": NCU_TRAFFIC_SOURCE,
         "kernel": "bbk::fft1d<C> (all 210 instantiations of the sweep, per-launch CUDA events)",
         "algorithmic_bytes_per_launch": "2*N*sizeof(complex)*M*K = 2 GiB",
         "per_size_frac": {"min": fracs[0], "median": fracs[len(fracs) // 2], "max": fracs[-1],
@@ -352,6 +389,12 @@ def main():
                        "sample": sample, "gbs": cgbs}
             except Exception as ex:  # the checker is optional for the measurement itself
                 cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        other = None
+        if world == 1 and not args.no_extra:
+            try:
+                other = other_configs(peak)
+            except Exception as ex:
+                other = {"error": str(ex)[:300]}
         line = {
             "metric": "c2c GFLOP/s (5N*log2N), 1d double-batched sweep N=2..512",
             "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -361,6 +404,7 @@ def main():
             "gbs": gbs, "gbs_frac_of_peak": gbs / world / peak,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * steps, "clocks": clocks,
+            "other_configs": other,
         }
         print(json.dumps(line))
     for _, _, _, p in plans:

@@ -692,27 +692,36 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
         constexpr int PAIRS = H / 2 + 1;
         constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        // all of the thread's loads are issued before the first pre-twiddle (memory-level
+        // parallelism, as in the first stage of the complex transform)
+        cx<T> x1[PCNT], x2[PCNT], wv[PCNT];
         static_for<0, PCNT>([&](auto cc) {
-            const int i = t + C::T * decltype(cc)::value;
+            constexpr int c = decltype(cc)::value;
+            const int i = t + C::T * c;
+            x1[c] = cx<T>{T(0), T(0)};
+            x2[c] = cx<T>{T(0), T(0)};
             if (i < PAIRS) {
-                cx<T> x1{T(0), T(0)}, x2{T(0), T(0)};
                 if constexpr (C::LOAD_STAGED) {
-                    x1 = sm[G::soff(b, i)];
-                    x2 = sm[G::soff(b, H - i)];
+                    x1[c] = sm[G::soff(b, i)];
+                    x2[c] = sm[G::soff(b, H - i)];
                 } else if (ok) {
-                    x1 = C::ld(a.in, m + u64(i) * C::is1(a) + k * C::is2(a));
-                    x2 = C::ld(a.in, m + u64(H - i) * C::is1(a) + k * C::is2(a));
+                    x1[c] = C::ld(a.in, m + u64(i) * C::is1(a) + k * C::is2(a));
+                    x2[c] = C::ld(a.in, m + u64(H - i) * C::is1(a) + k * C::is2(a));
                 }
-                if (i == 0) x1.y = T(0);
-                x2 = conj(x2);
-                const cx<T> w = ldg_cx(twr + i);
-                const cx<T> iw = cx<T>{-w.y, w.x};
-                const cx<T> aa = x1 + x2;
-                const cx<T> bb = cmul(x1 - x2, iw);
-                if constexpr (C::LOAD_STAGED) {
-                    // every pair must be read before slot i / h-i is overwritten by another
-                    // thread's pair only if pairs shared slots -- they do not (pair i owns {i, h-i})
-                }
+                wv[c] = ldg_cx(twr + i);
+            }
+        });
+        static_for<0, PCNT>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const int i = t + C::T * c;
+            if (i < PAIRS) {
+                cx<T> p1 = x1[c];
+                if (i == 0) p1.y = T(0);
+                const cx<T> p2 = conj(x2[c]);
+                const cx<T> iw = cx<T>{-wv[c].y, wv[c].x};
+                const cx<T> aa = p1 + p2;
+                const cx<T> bb = cmul(p1 - p2, iw);
+                // pair i owns the slots {i, h-i}: no other thread reads or writes them in this pass
                 sm[G::soff(b, i)] = aa + bb;
                 if (i != 0 && 2 * i != H) sm[G::soff(b, H - i)] = conj(aa - bb);
             }
@@ -756,15 +765,23 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         const bool okp = (m < C::M) && (2 * k < a.K);
         constexpr int PAIRS = C::N / 2 + 1;
         constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
+        cx<T> avs[PCNT], bvs[PCNT];
         static_for<0, PCNT>([&](auto cc) {
-            const int i = t + C::T * decltype(cc)::value;
+            constexpr int c = decltype(cc)::value;
+            const int i = t + C::T * c;
+            avs[c] = cx<T>{T(0), T(0)};
+            bvs[c] = cx<T>{T(0), T(0)};
+            if (i < PAIRS && okp) {
+                const u64 o = m + u64(i) * C::is1(a) + (2 * k) * C::is2(a);
+                avs[c] = C::ld(a.in, o);
+                if (2 * k + 1 < a.K) bvs[c] = C::ld(a.in, o + C::is2(a));
+            }
+        });
+        static_for<0, PCNT>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const int i = t + C::T * c;
             if (i < PAIRS) {
-                cx<T> av{T(0), T(0)}, bv{T(0), T(0)};
-                if (okp) {
-                    const u64 o = m + u64(i) * C::is1(a) + (2 * k) * C::is2(a);
-                    av = C::ld(a.in, o);
-                    if (2 * k + 1 < a.K) bv = C::ld(a.in, o + C::is2(a));
-                }
+                cx<T> av = avs[c], bv = bvs[c];
                 if (i == 0) {
                     av.y = T(0);
                     bv.y = T(0);

@@ -368,12 +368,13 @@ nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::
     std::size_t osize = cfg.ostride[dim_ + 1] * cfg.shape[dim_ + 1] * obytes;
     if (isize > osize) tmp_ = api_.create_device_buffer(isize);
 
-    // L2 blocking: run all passes over one block of outer k before moving to the next, with the
-    // block sized to stay resident in the 126 MB L2.  Passes 2..d then read what the previous pass
-    // just wrote from L2 and overwrite it in place, so HBM sees roughly one read of the input and
-    // one write of the output instead of one round trip per pass (reference nd_fft.hpp:140-152
-    // runs every pass over the whole tensor).  BBFFT_CUDA_ND_BLOCK_BYTES overrides; 0 disables.
-    std::size_t block_bytes = std::size_t(24) << 20;
+    // Optional L2 blocking (BBFFT_CUDA_ND_BLOCK_BYTES=<bytes>, off by default): run all steps over
+    // one block of outer k before moving to the next, so that later steps read what the previous
+    // step just wrote from the 126 MB L2.  Measured on the B200 it LOSES (3d fp64 64^3 K=64:
+    // 191 us unblocked, 242 us with 32 MiB blocks, 462 us with 8 MiB blocks -- profiles/
+    // r01c_nd_block.txt): a block is only one or two waves of CTAs, and the drain at every kernel
+    // boundary costs more than the L2 hits save.  Kept as a switch for other shapes.
+    std::size_t block_bytes = 0;
     if (char const *e = std::getenv("BBFFT_CUDA_ND_BLOCK_BYTES")) block_bytes = std::strtoull(e, nullptr, 10);
     std::size_t per_k = std::max(cfg.istride[dim_ + 1] * ibytes, cfg.ostride[dim_ + 1] * obytes);
     kblock_ = K_;

@@ -377,6 +377,25 @@ char const *wisdom_lookup(int fp, int n) {
     }
     return nullptr;
 }
+
+// Measured overrides for single configurations outside the c2c M=16 sweep (tools/exp_real_m1.py,
+// profiles/r01c_exp_m1.txt): {transform type, bytes per real, user-visible N, M, tune}.
+struct wisdom_special {
+    int type, fp, n;
+    std::uint64_t M;
+    char const *tune;
+};
+const wisdom_special wisdom_specials[] = {
+    {0, 4, 64, 1, "R=8x8,T=8,BH=16,ST=1,MB=2"},   // BASELINE config 1 shape: 6470 GB/s (heuristic 6316)
+    {1, 4, 256, 1, "R=16x8,T=8,BH=16,MB=2"},      // config 3 r2c: 5702 GB/s (heuristic 5457)
+    {2, 4, 256, 1, "R=8x16,T=16,BH=8,LD=0,ST=0,MB=4"},// config 3 c2r: 5793 GB/s (heuristic 4588)
+};
+char const *wisdom_special_lookup(int type, int fp, std::uint64_t n, std::uint64_t M) {
+    for (auto const &w : wisdom_specials) {
+        if (w.type == type && w.fp == fp && std::uint64_t(w.n) == n && w.M == M) return w.tune;
+    }
+    return nullptr;
+}
 } // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -398,7 +417,13 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         // BBFFT_CUDA_NO_WISDOM=1 turns it off (used by the tuner).
         char const *off = std::getenv("BBFFT_CUDA_NO_WISDOM");
         const std::uint64_t clen = (prob.type != 0 && prob.N % 2 == 0) ? prob.N / 2 : prob.N;
-        char const *w = !(off && *off == '1') ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
+        const bool use = !(off && *off == '1');
+        if (char const *sp = use ? wisdom_special_lookup(prob.type, prob.fp, prob.N, prob.M) : nullptr) {
+            for (auto const &kv : parse_tune(sp)) {
+                if (!tune.count(kv.first)) tune[kv.first] = kv.second;
+            }
+        }
+        char const *w = use ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
         if (w && *w) {
             auto wt = parse_tune(w);
             int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;

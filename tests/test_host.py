@@ -98,3 +98,45 @@ def test_generate_kernels_and_nvrtc_cross_compile(pkg):
     assert cubin[:4] == b"\x7fELF" and len(cubin) > 4096
     for n in names:
         assert n.encode() in cubin
+
+
+def test_register_cap_models_the_four_register_file_partitions(pkg):
+    """reg_cap (planner.cpp): the __maxnreg__ the planner emits must make `mb` CTAs resident under
+    the per-partition register model -- 7-warp CTAs at 136 registers only fit once per SM although
+    2 x 224 x 136 < 65536 (measured: the 2x slowdown of profiles/r01b_*)."""
+    d = pkg.describe(pkg.make_config(1, [16, 135, 64], 8, inplace=False), "R=9x15,T=9,ML=8,BH=3,MB=2")
+    m = re.search(r"BBK_MAXNREG\((\d+)\)", d["source"])
+    assert m and int(m.group(1)) == 128 and d["threads"] == 216
+    d = pkg.describe(pkg.make_config(1, [16, 135, 64], 8, inplace=False), "R=9x15,T=9,ML=8,BH=3,MB=1")
+    assert int(re.search(r"BBK_MAXNREG\((\d+)\)", d["source"]).group(1)) == 255
+
+
+def test_builtin_bundle_meets_planned_occupancy(pkg):
+    """Every kernel of the nvcc-built ahead-of-time bundle fits the occupancy the planner asked
+    for (identifier field _mb<k>) under the per-partition register model, and spills at most a few
+    words.  Runs without a GPU (cuobjdump reads the cubins)."""
+    import glob
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    cubins = sorted(glob.glob(os.path.join(ROOT, "double-batched-fft-library_b200", "builtin_kernels_*.cubin")))
+    assert cubins, "build() has not produced the built-in bundle"
+    seen = 0
+    for f in cubins:
+        out = subprocess.run(["cuobjdump", "-res-usage", f], capture_output=True, text=True).stdout
+        for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", out):
+            name, reg, stack = m.group(1), int(m.group(2)), int(m.group(3))
+            seen += 1
+            mb = int(re.search(r"_mb(\d+)_", name).group(1))
+            th = re.search(r"_th(\d+)_", name)
+            if th:
+                threads = int(th.group(1))
+            else:
+                t, ml, bh = (int(re.search(r"_%s(\d+)_" % k, name).group(1)) for k in ("T", "ML", "BH"))
+                threads = t * ml * bh
+            warps = (threads + 31) // 32
+            warps_per_partition = 16384 // (((reg + 7) // 8 * 8) * 32)
+            assert warps_per_partition // ((warps + 3) // 4) >= mb, (name, reg)
+            assert stack <= 128, (name, stack)
+    assert seen >= 216

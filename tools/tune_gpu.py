@@ -89,78 +89,92 @@ def main():
     ap.add_argument("--bytes", type=int, default=1 << 30)
     ap.add_argument("--out", default="gpurun_out/wisdom.json")
     ap.add_argument("--threads", type=int, default=min(32, os.cpu_count() or 8))
-    ap.add_argument("--budget", type=float, default=1e9, help="stop after this many seconds")
+    ap.add_argument("--from-csv", default="", help="per-size CSV of bench.py: tune only the (fp, N) below --below")
+    ap.add_argument("--below", type=float, default=0.9)
+    ap.add_argument("--batch", type=int, default=24, help="sizes compiled ahead and then timed back to back")
     args = ap.parse_args()
-    sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [n for n in aot.smooth_sizes() if n >= args.minN]
+    todo = []
+    if args.from_csv:
+        import csv
+        for r in csv.DictReader(open(args.from_csv)):
+            if float(r["frac_of_peak"]) < args.below:
+                todo.append((int(r["fp"]), int(r["N"])))
+    else:
+        sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [n for n in aot.smooth_sizes() if n >= args.minN]
+        todo = [(int(f), n) for f in args.fp.split(",") for n in sizes]
     stream = torch.cuda.current_stream().cuda_stream
     M = args.M
     results = {}
-    t_start = time.time()
     pool = ThreadPoolExecutor(args.threads)
     xbuf = {4: torch.rand(args.bytes // 4, dtype=torch.float32, device="cuda"),
             8: torch.rand(args.bytes // 8, dtype=torch.float64, device="cuda")}
     ybuf = {4: torch.empty_like(xbuf[4]), 8: torch.empty_like(xbuf[8])}
-    for fp in [int(f) for f in args.fp.split(",")]:
-        for n in sizes:
-            if time.time() - t_start > args.budget:
-                break
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+
+    def timed(plan, x, y, n):
+        e0.record()
+        for _ in range(n):
+            plan.execute(x, y)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # Sustained-clock tuning: all candidates of a batch of sizes are compiled first, then timed
+    # back to back without host gaps, so the GPU sits at its power-capped clocks like it does in
+    # the benchmark sweep (burst timings favour register-starved, spill-heavy variants that lose
+    # once the SM clock drops).
+    for b0 in range(0, len(todo), args.batch):
+        batch = todo[b0:b0 + args.batch]
+        jobs = []
+        for fp, n in batch:
             K = max(1, args.bytes // (M * n * 2 * fp))
             cfg = pkg.make_config(1, [M, n, K], fp, pkg.FORWARD, pkg.C2C, inplace=False)
-            cands = candidates(n, fp, M)
+            for tune in candidates(n, fp, M):
+                jobs.append((fp, n, K, cfg, tune))
 
-            def mk(tune):
-                try:
-                    return tune, pkg.Plan(cfg, stream=stream, tune=tune)
-                except Exception as ex:
-                    return tune, None
-            plans = list(pool.map(mk, cands))
+        def mk(job):
+            fp, n, K, cfg, tune = job
+            try:
+                return job, pkg.Plan(cfg, stream=stream, tune=tune)
+            except Exception:
+                return job, None
+        built = [(j, p) for j, p in pool.map(mk, jobs) if p is not None]
+        # heat up
+        if built:
+            j, p = built[0]
+            for _ in range(300):
+                p.execute(xbuf[j[0]], ybuf[j[0]])
+        per = {}
+        for (fp, n, K, cfg, tune), plan in built:
             x, y = xbuf[fp], ybuf[fp]
-            timings = []
-            for tune, plan in plans:
-                if plan is None:
-                    continue
-                for _ in range(2):
-                    plan.execute(x, y)
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                best = 1e9
-                for _ in range(3):
-                    e0.record()
-                    plan.execute(x, y)
-                    e1.record()
-                    e1.synchronize()
-                    best = min(best, e0.elapsed_time(e1))
-                timings.append((best, tune, plan.kernel_names[0], plan))
-            timings.sort(key=lambda t: t[0])
-            # second pass over the front-runners: median of 9 launches decides (best-of-3 is noisy)
+            plan.execute(x, y)
+            t = timed(plan, x, y, 6)
+            per.setdefault((fp, n), []).append([t, tune, plan, K])
+        for (fp, n), lst in per.items():
+            lst.sort(key=lambda t: t[0])
+            x, y = xbuf[fp], ybuf[fp]
             finals = []
-            for best, tune, name, plan in timings[:4]:
-                ts = []
-                for _ in range(9):
-                    e0.record()
-                    plan.execute(x, y)
-                    e1.record()
-                    e1.synchronize()
-                    ts.append(e0.elapsed_time(e1))
-                ts.sort()
-                finals.append((ts[4], tune, name, plan))
+            for t, tune, plan, K in lst[:4]:
+                finals.append([timed(plan, x, y, 40), tune, plan, K])
             finals.sort(key=lambda t: t[0])
-            timings = finals + timings[4:]
-            for t in timings:
-                t[3].close()
+            lst = finals + lst[4:]
+            K = lst[0][3]
             nbytes = 2.0 * M * n * K * 2 * fp
-            default = [t for t in timings if t[1] == ""]
-            best = timings[0]
+            default = [t for t in lst if t[1] == ""]
+            best = lst[0]
             results["%d,%d" % (fp, n)] = {"best": best[1], "gbs": nbytes / best[0] * 1e-6,
                                           "default_gbs": nbytes / default[0][0] * 1e-6 if default else None,
-                                          "top": [(t[1], round(nbytes / t[0] * 1e-6)) for t in timings[:5]],
-                                          "n_cands": len(timings)}
+                                          "top": [(t[1], round(nbytes / t[0] * 1e-6)) for t in lst[:5]],
+                                          "n_cands": len(lst), "mode": "sustained"}
             print(fp, n, "best %s %.0f GB/s (default %.0f) of %d cands; top: %s" % (
-                best[1], nbytes / best[0] * 1e-6, nbytes / default[0][0] * 1e-6 if default else -1, len(timings),
+                best[1], nbytes / best[0] * 1e-6, nbytes / default[0][0] * 1e-6 if default else -1, len(lst),
                 results["%d,%d" % (fp, n)]["top"][1:4]), flush=True)
-            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
-            with open(args.out, "w") as f:
-                json.dump(results, f, indent=1)
+        for _, plan in built:
+            plan.close()
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(results, f, indent=1)
 
 
 if __name__ == "__main__":
