@@ -554,6 +554,298 @@ template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const
     }
 }
 
+// stages S..END-1, all of them writing to shared memory (the caller runs stage END itself)
+template <class C, int S, int END, int SRC0>
+BBK_DEV void run_front_stages(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+    if constexpr (S < END) {
+        constexpr int SRC = (S == 0) ? SRC0 : IO_SMEM;
+        if constexpr (S > 0) {
+            BBK_SYNC();
+        }
+        run_stage<C, S, SRC, IO_SMEM>(a, sm, t, b, m, k, ok);
+        run_front_stages<C, S + 1, END, SRC0>(a, sm, t, b, m, k, ok);
+    }
+}
+
+// inverse of bin_of_sub: the last-stage sub-FFT whose first output bin is k0
+template <class C> BBK_DEV int sub_of_bin(int k0) {
+    int u = 0, rem = k0;
+    static_for<0, C::L - 1>([&](auto ss) {
+        constexpr int s = decltype(ss)::value;
+        u = u * C::radix(s) + rem % C::radix(s);
+        rem /= C::radix(s);
+    });
+    return u;
+}
+
+// ------------------------------------------------------------------------------------------
+// Real transforms with the pre / post pass fused into the first / last stage.
+//
+// Both real schemes pair element i with element NN - i (NN = complex length).  In the LAST stage
+// (radix R, NB = NN/R sub-FFTs) the sub-FFT with first bin k0 produces the bins k0 + NB q, and
+// their partners NN - k0 - NB q = (NB - k0) + NB (R-1-q) all come out of the sub-FFT with first
+// bin NB - k0.  In the FIRST stage (NS1 = NN/R sub-FFTs) sub-FFT u consumes the positions
+// u + NS1 j, whose partners (NS1 - u) + NS1 (R-1-j) feed sub-FFT NS1 - u.  A thread that runs a
+// sub-FFT together with its mirror therefore holds every pair in registers: the post-twiddle of
+// r2c and the pre-twiddle of c2r need no extra trip through shared memory and no extra barrier.
+// Units p = 0 .. NB/2 (resp. NS1/2); p = 0 and 2p = NB are their own mirrors.
+// ------------------------------------------------------------------------------------------
+template <class C, int SRC>
+BBK_DEV void r2c_last_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    constexpr int S = C::L - 1;
+    constexpr int R = C::radix(S);
+    constexpr int NN = C::N;
+    constexpr int NB = NN / R;
+    constexpr int UNITS = NB / 2 + 1;
+    constexpr int CNTU = (UNITS + C::T - 1) / C::T;
+    constexpr bool HALF = (C::MODE == R2C_HALF);
+    using WR = typename C::template WR<S>;
+    const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+
+    auto fetch = [&](cx<T> *v, int u) {
+        static_for<0, R>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            if constexpr (SRC == IO_SMEM) {
+                v[j] = sm[G::soff(b, u * R + j)];
+            } else {
+                v[j] = load_elem<C, SRC>(a, m, k, u * R + j, ok);
+            }
+        });
+    };
+    // yi = Y[i], yn = Y[NN - i]
+    auto emit = [&](int i, cx<T> yi, cx<T> yn) {
+        if constexpr (HALF) {
+            const cx<T> y2 = conj(yn);
+            const cx<T> w = ldg_cx(twr + i);
+            const cx<T> iw = cx<T>{-w.y, w.x};
+            const cx<T> aa = rmul(y2 + yi, T(0.5));
+            const cx<T> bb = cmul(rmul(y2 - yi, T(0.5)), iw);
+            if (ok) {
+                C::st(a.out, m + u64(i) * C::os1(a) + k * C::os2(a), aa + bb);
+                // X[NN] comes out of the pair (0, 0); the pair (NN/2, NN/2) has one member
+                if (2 * i != NN) {
+                    C::st(a.out, m + u64(NN - i) * C::os1(a) + k * C::os2(a), conj(aa - bb));
+                }
+            }
+        } else {
+            // rows 2k, 2k+1: A[idx] = (conj(Y[N-idx]) + Y[idx])/2, B[idx] = i (conj(Y[N-idx]) - Y[idx])/2
+            const bool low = 2 * i <= NN;
+            const int idx = low ? i : NN - i;
+            const cx<T> y1 = low ? yi : yn;
+            const cx<T> y2 = conj(low ? yn : yi);
+            const cx<T> av = rmul(y2 + y1, T(0.5));
+            const cx<T> d = rmul(y2 - y1, T(0.5));
+            if (ok) {
+                const u64 o = m + u64(idx) * C::os1(a) + (2 * k) * C::os2(a);
+                C::st(a.out, o, av);
+                if (2 * k + 1 < a.K) C::st(a.out, o + C::os2(a), cx<T>{-d.y, d.x});
+            }
+        }
+    };
+
+    static_for<0, CNTU>([&](auto cc) {
+        const int p = t + C::T * decltype(cc)::value;
+        if (UNITS % C::T == 0 || p < UNITS) {
+            const int kb = (NB - p) % NB;
+            cx<T> va[R], vb[R];
+            fetch(va, sub_of_bin<C>(p));
+            if (kb != p) fetch(vb, sub_of_bin<C>(kb));
+            if constexpr (SRC != IO_SMEM) {
+                // single-stage kernels read and write global memory only: in-place rows of
+                // different m overlap, so every load of the CTA precedes its first store
+                BBK_SYNC();
+            }
+            reg_fft<T, WR, R, C::DIR>::run(va);
+            if (kb != p) {
+                reg_fft<T, WR, R, C::DIR>::run(vb);
+                static_for<0, R>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    emit(p + NB * q, va[q], vb[R - 1 - q]);
+                });
+            } else if (p == 0) {
+                emit(0, va[0], va[0]);
+                static_for<1, (R + 1) / 2>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    emit(NB * q, va[q], va[R - q]);
+                });
+                if constexpr (R % 2 == 0) {
+                    emit(NB * (R / 2), va[R / 2], va[R / 2]);
+                }
+            } else {
+                // 2p == NB: bins p + NB q pair with p + NB (R-1-q)
+                static_for<0, R / 2>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
+                    emit(p + NB * q, va[q], va[R - 1 - q]);
+                });
+                if constexpr (R % 2 == 1) {
+                    emit(p + NB * ((R - 1) / 2), va[(R - 1) / 2], va[(R - 1) / 2]);
+                }
+            }
+        } else if constexpr (SRC != IO_SMEM) {
+            BBK_SYNC();
+        }
+    });
+}
+
+template <class C, int DST>
+BBK_DEV void c2r_first_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    constexpr int R = C::radix(0);
+    constexpr int NN = C::N;
+    constexpr int NS1 = NN / R;
+    constexpr int UNITS = NS1 / 2 + 1;
+    constexpr int CNTU = (UNITS + C::T - 1) / C::T;
+    constexpr bool HALF = (C::MODE == C2R_HALF);
+    constexpr bool LAST = (C::L == 1);
+    using WR = typename C::template WR<0>;
+    const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + C::tw_off(0);
+    const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+
+    // spectrum element i of this thread's column (half mode), or rows A / B of the slice pair
+    auto ldx = [&](int i) { return C::ld(a.in, m + u64(i) * C::is1(a) + k * C::is2(a)); };
+    // half mode: xa[j] = X[p + NS1 j], xb[j] = X[ub + NS1 j] (p == 0: xb[0] = X[NN])
+    // double mode: pair j of the unit is (i, NN - i) with i = p + NS1 j; xa[j] = A[min], xb[j] = B[min]
+    cx<T> xa[CNTU][R], xb[CNTU][R];
+    static_for<0, CNTU>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int p = t + C::T * c;
+        static_for<0, R>([&](auto jj) {
+            constexpr int j = decltype(jj)::value;
+            xa[c][j] = cx<T>{T(0), T(0)};
+            xb[c][j] = cx<T>{T(0), T(0)};
+        });
+        if ((UNITS % C::T == 0 || p < UNITS) && ok) {
+            const int ub = (NS1 - p) % NS1;
+            if constexpr (HALF) {
+                static_for<0, R>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    xa[c][j] = ldx(p + NS1 * j);
+                });
+                if (ub != p) {
+                    static_for<0, R>([&](auto jj) {
+                        constexpr int j = decltype(jj)::value;
+                        xb[c][j] = ldx(ub + NS1 * j);
+                    });
+                } else if (p == 0) {
+                    xb[c][0] = ldx(NN);
+                }
+            } else {
+                // NN is odd: only p == 0 is its own mirror
+                static_for<0, R>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    const int i = p + NS1 * j;
+                    const int idx = 2 * i <= NN ? i : NN - i;
+                    // the mirror unit's pairs are the same pairs: for p == 0 only j <= R/2 is new
+                    if (ub != p || j <= R / 2) {
+                        const u64 o = m + u64(idx) * C::is1(a) + (2 * k) * C::is2(a);
+                        xa[c][j] = C::ld(a.in, o);
+                        if (2 * k + 1 < a.K) xb[c][j] = C::ld(a.in, o + C::is2(a));
+                    }
+                });
+            }
+        }
+    });
+    if constexpr (LAST) {
+        BBK_SYNC(); // in-place rows of different m overlap: loads of the CTA before its stores
+    }
+    // z[i], z[NN-i] from the pair (half mode: X[i], X[NN-i]; double mode: A[idx], B[idx])
+    auto pre = [&](int i, cx<T> u1, cx<T> u2, cx<T> &zi, cx<T> &zn) {
+        if constexpr (HALF) {
+            cx<T> x1 = u1;
+            if (i == 0) x1.y = T(0);
+            const cx<T> x2 = conj(u2);
+            const cx<T> w = ldg_cx(twr + i);
+            const cx<T> iw = cx<T>{-w.y, w.x};
+            const cx<T> aa = x1 + x2;
+            const cx<T> bb = cmul(x1 - x2, iw);
+            zi = aa + bb;
+            zn = conj(aa - bb);
+        } else {
+            cx<T> av = u1, bv = u2;
+            if (i == 0) {
+                av.y = T(0);
+                bv.y = T(0);
+            }
+            const cx<T> ylo = cx<T>{av.x - bv.y, av.y + bv.x}; // Y[idx]
+            const cx<T> yhi = cx<T>{av.x + bv.y, bv.x - av.y}; // Y[NN - idx]
+            const bool low = 2 * i <= NN;
+            zi = low ? ylo : yhi;
+            zn = low ? yhi : ylo;
+        }
+    };
+    auto finish = [&](cx<T> *w, int u) {
+        reg_fft<T, WR, R, C::DIR>::run(w);
+        if constexpr (!LAST) {
+            static_for<1, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                w[q] = cmul(w[q], ldg_cx(tw + (q - 1) * NS1 + u));
+            });
+            static_for<0, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                sm[G::soff(b, u + NS1 * q)] = w[q];
+            });
+        } else {
+            static_for<0, R>([&](auto qq) {
+                constexpr int q = decltype(qq)::value;
+                store_elem<C, DST>(a, m, k, q, w[q], ok); // single stage: NS1 == 1, u == 0
+            });
+        }
+    };
+    static_for<0, CNTU>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const int p = t + C::T * c;
+        if (UNITS % C::T == 0 || p < UNITS) {
+            const int ub = (NS1 - p) % NS1;
+            cx<T> za[R], zb[R];
+            cx<T> dummy;
+            if (ub != p) {
+                static_for<0, R>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    if constexpr (HALF) {
+                        pre(p + NS1 * j, xa[c][j], xb[c][R - 1 - j], za[j], zb[R - 1 - j]);
+                    } else {
+                        pre(p + NS1 * j, xa[c][j], xb[c][j], za[j], zb[R - 1 - j]);
+                    }
+                });
+                finish(za, p);
+                finish(zb, ub);
+            } else if (p == 0) {
+                if constexpr (HALF) {
+                    pre(0, xa[c][0], xb[c][0], za[0], dummy);
+                } else {
+                    pre(0, xa[c][0], xb[c][0], za[0], dummy);
+                }
+                static_for<1, (R + 1) / 2>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    if constexpr (HALF) {
+                        pre(NS1 * j, xa[c][j], xa[c][R - j], za[j], za[R - j]);
+                    } else {
+                        pre(NS1 * j, xa[c][j], xb[c][j], za[j], za[R - j]);
+                    }
+                });
+                if constexpr (R % 2 == 0) {
+                    // half mode only (NN even): i == NN/2 is its own partner
+                    pre(NS1 * (R / 2), xa[c][R / 2], xa[c][R / 2], za[R / 2], dummy);
+                }
+                finish(za, 0);
+            } else {
+                // 2p == NS1 (half mode only): positions p + NS1 j pair with p + NS1 (R-1-j)
+                static_for<0, R / 2>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    pre(p + NS1 * j, xa[c][j], xa[c][R - 1 - j], za[j], za[R - 1 - j]);
+                });
+                if constexpr (R % 2 == 1) {
+                    pre(p + NS1 * ((R - 1) / 2), xa[c][(R - 1) / 2], xa[c][(R - 1) / 2], za[(R - 1) / 2], dummy);
+                }
+                finish(za, p);
+            }
+        }
+    });
+}
+
 // Cooperative, coalesced copy of the CTA's batch of rows between global and shared memory.
 // NROW = row length in elements of type E, rows are addressed (m, n, k) -> m + n*s1 + k*s2.
 template <class C, class E, int NROW, bool TO_SMEM, bool REVERSE, class LD, class ST>
@@ -631,6 +923,17 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // a = (conj(Y[h-i]) + Y[i])/2, b = (conj(Y[h-i]) - Y[i])/2 * (i w_N^i)
         // (reference: src/base/generator/sbfft_gen.cpp:180-200, f2fft_gen.cpp:253-271)
         constexpr int H = C::N;
+        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+            // post-twiddle fused into the last stage (registers only)
+            if constexpr (C::L == 1) {
+                r2c_last_stage<C, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
+            } else {
+                run_front_stages<C, 0, C::L - 1, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
+                BBK_SYNC();
+                r2c_last_stage<C, IO_SMEM>(a, sm, t, b, m, k, ok);
+            }
+            return;
+        }
         if constexpr (C::LOAD_STAGED) {
             // M == 1: a real row is H aligned complex words
             coop_copy<C, cx<T>, H, true, false>(
@@ -683,6 +986,14 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // a = x1 + x2, b = (x1 - x2) * (i w_N^i); x[2j], x[2j+1] = Re, Im of IFFT_h(z)[j]
         // (reference: src/base/generator/sbfft_gen.cpp:221-247, f2fft_gen.cpp:349-409)
         constexpr int H = C::N;
+        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+            // pre-twiddle fused into the first stage (registers only)
+            c2r_first_stage<C, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
+            if constexpr (C::L > 1) {
+                run_stages<C, 1, IO_SMEM, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
+            }
+            return;
+        }
         if constexpr (C::LOAD_STAGED) {
             coop_copy<C, cx<T>, H + 1, true, false>(
                 sm, m0, k0, C::M, a.K, C::is1(a), C::is2(a), tid,
@@ -742,6 +1053,16 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // A[i] = (conj(Y[N-i]) + Y[i])/2, B[i] = i (conj(Y[N-i]) - Y[i])/2, i <= N/2
         // (reference: src/base/generator/sbfft_gen.cpp:274-291, f2fft_gen.cpp:314-330)
         const bool okp = (m < C::M) && (2 * k < a.K);
+        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+            if constexpr (C::L == 1) {
+                r2c_last_stage<C, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
+            } else {
+                run_front_stages<C, 0, C::L - 1, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
+                BBK_SYNC();
+                r2c_last_stage<C, IO_SMEM>(a, sm, t, b, m, k, okp);
+            }
+            return;
+        }
         run_stages<C, 0, IO_G_2ROWS, IO_SMEM>(a, sm, t, b, m, k, okp);
         BBK_SYNC();
         constexpr int PAIRS = C::N / 2 + 1;
@@ -763,6 +1084,13 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // Y[i] = A[i] + i B[i], Y[N-i] = conj(A[i]) + i conj(B[i]); rows 2k, 2k+1 = Re, Im of IFFT_N(Y)
         // (reference: src/base/generator/sbfft_gen.cpp:318-351, f2fft_gen.cpp:443-502)
         const bool okp = (m < C::M) && (2 * k < a.K);
+        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+            c2r_first_stage<C, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
+            if constexpr (C::L > 1) {
+                run_stages<C, 1, IO_SMEM, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
+            }
+            return;
+        }
         constexpr int PAIRS = C::N / 2 + 1;
         constexpr int PCNT = (PAIRS + C::T - 1) / C::T;
         cx<T> avs[PCNT], bvs[PCNT];

@@ -427,11 +427,24 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         if (w && *w) {
             auto wt = parse_tune(w);
             int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;
-            // real in-place transforms need all m of a k slice in one CTA (see inplace_unsupported)
-            const bool covers = prob.type == 0 || std::uint64_t(wml) >= prob.M;
-            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0 && covers) {
+            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
+                // Real in-place transforms need all m of a k slice in one CTA (see
+                // inplace_unsupported): when the entry's lanes do not cover M, keep its radices and
+                // threads per transform but widen the lanes to the default (the CTA keeps its size
+                // by shrinking the batch), and let the heuristic choose the register cap.
+                const int full = 128 / (2 * prob.fp);
+                const int dml = std::min(pow2_ceil(prob.M), full);
+                const bool widen = prob.type != 0 && std::uint64_t(wml) < prob.M && dml > wml && prob.M % dml == 0;
                 for (auto const &kv : wt) {
-                    if (!tune.count(kv.first)) tune[kv.first] = kv.second;
+                    if (tune.count(kv.first)) continue;
+                    if (widen && kv.first == "MB") continue;
+                    if (widen && kv.first == "ML") {
+                        tune["ML"] = std::to_string(dml);
+                    } else if (widen && kv.first == "BH") {
+                        tune["BH"] = std::to_string(std::max(1, std::atoi(kv.second.c_str()) * wml / dml));
+                    } else {
+                        tune[kv.first] = kv.second;
+                    }
                 }
             }
         }
@@ -741,7 +754,8 @@ std::vector<double> make_twiddles(kernel_params const &p) {
     if (p.mode == k_r2c_half || p.mode == k_c2r_half) {
         // post/pre twiddles for the half-length trick: w_{2N}^{dir*i}, i = 0..N/2
         // (reference host table: src/common/algorithm/factor2_slm_fft.hpp:81-88)
-        for (int i = 0; i <= p.N / 2; ++i) {
+        // (the fused first/last stages pair i with N-i for every i, so the table runs to N)
+        for (int i = 0; i <= p.N; ++i) {
             double re, im;
             unit_root(i, 2L * p.N, p.dir, re, im);
             tw.push_back(re);

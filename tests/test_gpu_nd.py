@@ -70,7 +70,7 @@ def test_r2c_c2r_nd(pkg, fp, inplace, M, Ns, K):
         buf = torch.from_numpy(xin).cuda()
         plan.execute(buf)
         torch.cuda.synchronize()
-        spec = buf.cpu().numpy().view(cdtype(fp)).reshape(spec_shape)
+        spec = buf.cpu().numpy().reshape(-1).view(cdtype(fp)).reshape(spec_shape)
     else:
         xd = torch.from_numpy(xin).cuda()
         yd = torch.zeros(spec_shape, dtype=torch.complex64 if fp == 4 else torch.complex128, device="cuda")
@@ -92,7 +92,7 @@ def test_r2c_c2r_nd(pkg, fp, inplace, M, Ns, K):
         buf = torch.from_numpy(raw).cuda()
         plan.execute(buf)
         torch.cuda.synchronize()
-        back = buf.cpu().numpy().view(rdtype(fp)).reshape(xin.shape)[..., :N1, :]
+        back = buf.cpu().numpy().reshape(-1).view(rdtype(fp)).reshape(xin.shape)[..., :N1, :]
     else:
         sd = torch.from_numpy(np.ascontiguousarray(sp)).cuda()
         od = torch.zeros(x.shape, dtype=torch.float32 if fp == 4 else torch.float64, device="cuda")

@@ -56,10 +56,11 @@ def candidates(n, fp, M):
                 cands.append("R=%d,T=1,BH=%d" % (f[0], bh))
             continue
         ts = set()
-        for c in (1, 2):
-            t = -(-(n // max(f)) // c)
+        # threads per transform: one sub-FFT per thread in the largest-radix stage (and half of
+        # that), and one per thread in EVERY stage (n / smallest radix: fewest registers)
+        for t in (n // max(f), -(-(n // max(f)) // 2), n // min(f)):
             regs = max(-(-(n // r) // t) * r for r in f)
-            if regs <= (32 if fp == 4 else 20):
+            if regs <= (32 if fp == 4 else 25):
                 ts.add(t)
         for t in ts:
             for ml in {full, max(2, full // 2)}:
