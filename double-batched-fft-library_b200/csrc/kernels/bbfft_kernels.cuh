@@ -311,7 +311,7 @@ template <class T, class W, int R, int DIR> struct reg_fft {
 //   real_t, N (complex FFT length run by the stages), NREAL (user-visible length for real
 //   modes), DIR, MODE, L (stages), radix(s), T (threads per transform), ML (batch lanes, the
 //   fastest thread index), BH (further batch entries per CTA), KLANES (batch lanes index k
-//   instead of m; only for M == 1), M, LOAD_STAGED / STORE_STAGED, smem layout LL / PADK /
+//   instead of m; only for M == 1), M, LOAD_STAGED / STORE_STAGED, REAL_FUSED, smem layout LL / PADK /
 //   ROW, twiddle block offsets tw_off(s), WR<s> table types, is1()..os2() stride accessors and
 //   the ld/st hooks.
 // ------------------------------------------------------------------------------------------
@@ -923,7 +923,7 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // a = (conj(Y[h-i]) + Y[i])/2, b = (conj(Y[h-i]) - Y[i])/2 * (i w_N^i)
         // (reference: src/base/generator/sbfft_gen.cpp:180-200, f2fft_gen.cpp:253-271)
         constexpr int H = C::N;
-        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+        if constexpr (C::REAL_FUSED) {
             // post-twiddle fused into the last stage (registers only)
             if constexpr (C::L == 1) {
                 r2c_last_stage<C, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
@@ -986,7 +986,7 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // a = x1 + x2, b = (x1 - x2) * (i w_N^i); x[2j], x[2j+1] = Re, Im of IFFT_h(z)[j]
         // (reference: src/base/generator/sbfft_gen.cpp:221-247, f2fft_gen.cpp:349-409)
         constexpr int H = C::N;
-        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+        if constexpr (C::REAL_FUSED) {
             // pre-twiddle fused into the first stage (registers only)
             c2r_first_stage<C, IO_G_RPAIR>(a, sm, t, b, m, k, ok);
             if constexpr (C::L > 1) {
@@ -1053,7 +1053,7 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // A[i] = (conj(Y[N-i]) + Y[i])/2, B[i] = i (conj(Y[N-i]) - Y[i])/2, i <= N/2
         // (reference: src/base/generator/sbfft_gen.cpp:274-291, f2fft_gen.cpp:314-330)
         const bool okp = (m < C::M) && (2 * k < a.K);
-        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+        if constexpr (C::REAL_FUSED) {
             if constexpr (C::L == 1) {
                 r2c_last_stage<C, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
             } else {
@@ -1084,7 +1084,7 @@ template <class C> BBK_DEV void fft1d(args const &a) {
         // Y[i] = A[i] + i B[i], Y[N-i] = conj(A[i]) + i conj(B[i]); rows 2k, 2k+1 = Re, Im of IFFT_N(Y)
         // (reference: src/base/generator/sbfft_gen.cpp:318-351, f2fft_gen.cpp:443-502)
         const bool okp = (m < C::M) && (2 * k < a.K);
-        if constexpr (!C::LOAD_STAGED && !C::STORE_STAGED) {
+        if constexpr (C::REAL_FUSED) {
             c2r_first_stage<C, IO_G_2ROWS>(a, sm, t, b, m, k, okp);
             if constexpr (C::L > 1) {
                 run_stages<C, 1, IO_SMEM, IO_G_2ROWS>(a, sm, t, b, m, k, okp);

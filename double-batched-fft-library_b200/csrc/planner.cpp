@@ -137,7 +137,9 @@ void enum_factorizations(int n, int max_r, int max_l, std::vector<int> &cur,
     }
 }
 
-stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
+// mirror_max > 0 (fused real transforms): the factorization must contain a radix <= mirror_max for
+// the stage that holds a sub-FFT together with its mirror.
+stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mirror_max = 0) {
     const int single_max = (fp == 4) ? 32 : 16; // one thread holds the whole transform
     stage_choice best;
     best.cost = 1e30;
@@ -164,6 +166,7 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
         for (auto const &f : facs) {
             int L = int(f.size());
             if (L < 2 && N > 64) continue;
+            if (mirror_max > 0 && L > 1 && f.front() > mirror_max) continue; // f is ascending
             std::set<int> tcand;
             for (int r : f) {
                 for (int c = 1; c <= 8; ++c) {
@@ -197,6 +200,9 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform) {
                 }
             }
         }
+    }
+    if (best.radix.empty() && mirror_max > 0) {
+        return choose_stages(N, fp, max_threads_per_transform, 0);
     }
     if (best.radix.empty()) {
         throw std::runtime_error("bbfft-cuda planner: no factorization found for N=" +
@@ -389,10 +395,16 @@ const wisdom_special wisdom_specials[] = {
     {0, 4, 64, 1, "R=8x8,T=8,BH=16,ST=1,MB=2"},   // BASELINE config 1 shape: 6470 GB/s (heuristic 6316)
     {1, 4, 256, 1, "R=16x8,T=8,BH=16,MB=2"},      // config 3 r2c: 5702 GB/s (heuristic 5457)
     {2, 4, 256, 1, "R=8x16,T=16,BH=8,LD=0,ST=0,MB=4"},// config 3 c2r: 5793 GB/s (heuristic 4588)
+// measured r2c / c2r entries of the M = 16 real sweep (tools/tune_gpu.py --type r2c|c2r); they
+// keep full batch lanes, so they apply to every M that is a multiple of the lane count
+#include "wisdom_real.inc"
 };
 char const *wisdom_special_lookup(int type, int fp, std::uint64_t n, std::uint64_t M) {
     for (auto const &w : wisdom_specials) {
-        if (w.type == type && w.fp == fp && std::uint64_t(w.n) == n && w.M == M) return w.tune;
+        // M == 0 marks a lane-generic entry: any M that fills whole 128-byte rows
+        const std::uint64_t full = 128 / (2 * fp);
+        const bool m_ok = w.M == M || (w.M == 0 && M >= full && M % full == 0);
+        if (w.type == type && w.fp == fp && std::uint64_t(w.n) == n && m_ok) return w.tune;
     }
     return nullptr;
 }
@@ -410,6 +422,8 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         throw std::runtime_error("bbfft-cuda planner: N too large for the single-kernel path");
     }
     auto tune = parse_tune(tune_str);
+    // stage order is the caller's when it names the radices itself or a measured real entry does
+    bool keep_stage_order = tune.count("R") != 0;
     {
         // Measured wisdom (c2c sweep) applies when the batch rows fill the wisdom's lanes.  Real
         // transforms run the same stages on their complex length (N/2 for even N), so they take
@@ -418,35 +432,51 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         char const *off = std::getenv("BBFFT_CUDA_NO_WISDOM");
         const std::uint64_t clen = (prob.type != 0 && prob.N % 2 == 0) ? prob.N / 2 : prob.N;
         const bool use = !(off && *off == '1');
-        if (char const *sp = use ? wisdom_special_lookup(prob.type, prob.fp, prob.N, prob.M) : nullptr) {
+        char const *sp = use ? wisdom_special_lookup(prob.type, prob.fp, prob.N, prob.M) : nullptr;
+        if (sp) {
+            keep_stage_order = true;
             for (auto const &kv : parse_tune(sp)) {
                 if (!tune.count(kv.first)) tune[kv.first] = kv.second;
             }
         }
-        char const *w = use ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
+        // a measured entry for exactly this transform wins over the c2c entry of its length
+        char const *w = (use && !sp) ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
         if (w && *w) {
             auto wt = parse_tune(w);
             int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;
-            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
-                // Real in-place transforms need all m of a k slice in one CTA (see
-                // inplace_unsupported): when the entry's lanes do not cover M, keep its radices and
-                // threads per transform but widen the lanes to the default (the CTA keeps its size
-                // by shrinking the batch), and let the heuristic choose the register cap.
-                const int full = 128 / (2 * prob.fp);
-                const int dml = std::min(pow2_ceil(prob.M), full);
-                const bool widen = prob.type != 0 && std::uint64_t(wml) < prob.M && dml > wml && prob.M % dml == 0;
+            // a real transform inherits the c2c entry only if one of its radices is small enough
+            // for the mirrored stage, and never its register cap (its live set differs)
+            bool real_ok = true;
+            if (prob.type != 0 && wt.count("R")) {
+                auto rr = parse_radices(wt["R"]);
+                real_ok = rr.size() < 2 || *std::min_element(rr.begin(), rr.end()) <= (prob.fp == 4 ? 16 : 8);
+                wt.erase("MB");
+            }
+            if (real_ok && wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
                 for (auto const &kv : wt) {
-                    if (tune.count(kv.first)) continue;
-                    if (widen && kv.first == "MB") continue;
-                    if (widen && kv.first == "ML") {
-                        tune["ML"] = std::to_string(dml);
-                    } else if (widen && kv.first == "BH") {
-                        tune["BH"] = std::to_string(std::max(1, std::atoi(kv.second.c_str()) * wml / dml));
-                    } else {
-                        tune[kv.first] = kv.second;
-                    }
+                    if (!tune.count(kv.first)) tune[kv.first] = kv.second;
                 }
             }
+        }
+        // Real in-place transforms need all m of a k slice in one CTA (see inplace_unsupported).
+        // When the strides allow the spectrum to overlay the real rows (real k-stride = twice the
+        // complex one) and M fits one warp -- the cases the reference runs in place (Mb = pow2 >= M
+        // up to the sub-group size, src/base/generator/small_batch_fft.cpp:19-38) -- the lanes
+        // cover M: a measured entry keeps its radices and threads per transform, the CTA keeps its
+        // size by shrinking the batch, and the heuristic chooses the register cap.
+        const std::int64_t rs2 = prob.type == 1 ? prob.is2 : prob.os2;
+        const std::int64_t cs2 = prob.type == 1 ? prob.os2 : prob.is2;
+        const bool overlay = prob.type != 0 && rs2 == 2 * cs2;
+        if (overlay && prob.M > 1 && prob.M <= 32 && !parse_tune(tune_str).count("ML")) {
+            const int need = pow2_ceil(prob.M);
+            const int have = tune.count("ML") ? std::atoi(tune["ML"].c_str()) : need;
+            if (have != need) {
+                if (tune.count("BH")) {
+                    tune["BH"] = std::to_string(std::max(1, std::atoi(tune["BH"].c_str()) * have / need));
+                }
+                if (!parse_tune(tune_str).count("MB")) tune.erase("MB");
+            }
+            tune["ML"] = std::to_string(need);
         }
     }
     kernel_plan plan;
@@ -511,9 +541,19 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         if (prod != p.N) throw std::runtime_error("bbfft-cuda planner: tune R does not multiply to N");
         sc.T = sc.radix.size() == 1 ? 1 : p.N / maxr;
     } else {
-        sc = choose_stages(p.N, p.fp, max_tpt);
+        const bool fused_real = p.mode != k_c2c && prob.M > 1;
+        sc = choose_stages(p.N, p.fp, max_tpt, fused_real ? (p.fp == 4 ? 16 : 8) : 0);
     }
     if (tune.count("T")) sc.T = std::atoi(tune["T"].c_str());
+    if (p.mode != k_c2c && !keep_stage_order) {
+        // The fused post (r2c: last stage) / pre (c2r: first stage) pass keeps a sub-FFT and its
+        // mirror in registers, twice the live values of any other stage: give it the smallest radix.
+        if (p.mode == k_r2c_half || p.mode == k_r2c_double) {
+            std::sort(sc.radix.begin(), sc.radix.end(), std::greater<int>());
+        } else {
+            std::sort(sc.radix.begin(), sc.radix.end());
+        }
+    }
     p.L = int(sc.radix.size());
     if (p.L > 4) throw std::runtime_error("bbfft-cuda planner: more than 4 stages");
     for (int s = 0; s < 4; ++s) p.radix[s] = s < p.L ? sc.radix[s] : 1;
@@ -586,6 +626,13 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     // user callbacks see every element exactly once in either path, so staging stays legal.
     if (tune.count("LD")) p.load_staged = std::atoi(tune["LD"].c_str()) != 0;
     if (tune.count("ST")) p.store_staged = std::atoi(tune["ST"].c_str()) != 0;
+    // Real pre/post pass: fused into the first/last stage (a thread runs a sub-FFT and its mirror,
+    // no extra trip through shared memory) when the batch lanes walk m.  With t-lanes (M == 1) the
+    // mirrored units leave half of every warp idle in the stage that issues the global loads;
+    // measured on config 3 (c2r f32 N=256 M=1): 3519 GB/s fused vs 5400 GB/s as a separate pass
+    // (profiles/r01e_real_sweep.jsonl vs r01d), so those keep the separate pass.
+    p.real_fused = p.mode != k_c2c && !p.load_staged && !p.store_staged && p.ML > 1;
+    if (tune.count("RF")) p.real_fused = p.mode != k_c2c && !p.load_staged && !p.store_staged && std::atoi(tune["RF"].c_str()) != 0;
 
     choose_smem_layout(p);
     if (tune.count("PADK") || tune.count("ROW")) {
@@ -611,6 +658,14 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
             int nsub = p.N / p.radix[s];
             int cnt = (nsub + p.T - 1) / p.T;
             regs_complex = std::max(regs_complex, (s == 0 ? cnt : 1) * p.radix[s]);
+        }
+        if (p.real_fused) {
+            // fused real pre / post pass: a sub-FFT and its mirror are live together
+            const bool r2c = p.mode == k_r2c_half || p.mode == k_r2c_double;
+            const int rm = p.radix[r2c ? p.L - 1 : 0];
+            const int units = (p.N / rm) / 2 + 1;
+            const int cntu = r2c ? 1 : (units + p.T - 1) / p.T;
+            regs_complex = std::max(regs_complex, 2 * cntu * rm);
         }
         // measured: unconstrained kernels use ~1.6 registers per live 32-bit word + 20
         int words = (p.fp == 4 ? 2 : 4) * regs_complex;
@@ -651,7 +706,7 @@ std::string make_identifier(kernel_params const &p) {
     os << "_T" << p.T << "_ML" << p.ML << "_BH" << p.BH << "_mb" << p.min_blocks << "_kl" << int(p.klanes) << "_ld"
        << int(p.load_staged) << "_st" << int(p.store_staged) << "_pk" << p.PADK << "_row" << p.ROW
        << "_is" << p.is1 << "_" << p.is2 << "_os" << p.os1 << "_" << p.os2;
-    if (p.mode != k_c2c) os << "_pl" << int(p.pair_load) << "_ps" << int(p.pair_store);
+    if (p.mode != k_c2c) os << "_pl" << int(p.pair_load) << "_ps" << int(p.pair_store) << "_rf" << int(p.real_fused);
     if (!p.cb_load.empty()) os << "_" << p.cb_load;
     if (!p.cb_store.empty()) os << "_" << p.cb_store;
     std::string s = os.str();
@@ -816,7 +871,8 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
        << ", LOAD_STAGED = " << (p.load_staged ? "true" : "false")
        << ", STORE_STAGED = " << (p.store_staged ? "true" : "false")
        << ", PAIR_LOAD = " << (p.pair_load ? "true" : "false")
-       << ", PAIR_STORE = " << (p.pair_store ? "true" : "false") << ";\n";
+       << ", PAIR_STORE = " << (p.pair_store ? "true" : "false")
+       << ", REAL_FUSED = " << (p.real_fused ? "true" : "false") << ";\n";
     os << "    static constexpr bbk::u64 M = " << p.M << "ull;\n";
     os << "    static constexpr int LL = " << p.LL << ", PADK = " << p.PADK << ", ROW = " << p.ROW
        << ", TW_REAL = " << tw_total << ";\n";

@@ -45,6 +45,7 @@ struct kernel_params {
     int T = 1, ML = 1, BH = 1;
     bool klanes = false, load_staged = false, store_staged = false;
     bool pair_load = false, pair_store = false; // real side is read/written as aligned complex words
+    bool real_fused = false; // real pre/post pass fused into the first/last stage (mirrored sub-FFT pairs)
     std::uint64_t M = 1;
     std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1;
     int LL = 1, PADK = 0, ROW = 1;
@@ -72,7 +73,7 @@ struct kernel_plan {
     bool inplace_unsupported = false;
 };
 
-// Tuning overrides, "key=value,key=value" (keys: R=8x8, T, ML, BH, LD, ST, PADK, ROW, KL).
+// Tuning overrides, "key=value,key=value" (keys: R=8x8, T, ML, BH, MB, LD, ST, RF, PADK, ROW, KL).
 // Used by the auto-tuner and the tests; empty string = heuristics.
 kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
                            std::string const &tune = std::string());

@@ -7,8 +7,14 @@
 #include "bbfft/cuda/online_compiler.hpp"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <iterator>
 #include <mutex>
 #include <sstream>
 
@@ -71,8 +77,71 @@ nvrtc_api &nvrtc() {
 }
 } // namespace
 
+// ------------------------------------------------------------------------------------------
+// Persistent kernel cache (BBFFT_CUDA_KERNEL_CACHE=<dir>): cubins keyed by a hash of everything
+// that determines them (stub source incl. pasted user callbacks, device header text,
+// architecture, options).  The in-memory jit_cache of the reference (include/bbfft/jit_cache.hpp)
+// lives for one process; this one carries NVRTC results across processes -- and across machines
+// of the same image, which is how tools/tune_gpu.py ships pre-compiled candidates to the GPU box.
+// ------------------------------------------------------------------------------------------
+namespace {
+std::uint64_t fnv1a(std::uint64_t h, char const *p, std::size_t n) {
+    for (std::size_t i = 0; i < n; ++i) {
+        h ^= static_cast<unsigned char>(p[i]);
+        h *= 0x100000001b3ull;
+    }
+    return h;
+}
+std::string disk_cache_path(std::string const &source, std::string const &arch,
+                            std::vector<std::string> const &options) {
+    char const *dir = std::getenv("BBFFT_CUDA_KERNEL_CACHE");
+    if (!dir || !*dir) return {};
+    std::uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x84222325cbf29ce4ull;
+    char const *hdr = kernel_header_text();
+    h1 = fnv1a(h1, hdr, std::strlen(hdr));
+    h1 = fnv1a(h1, source.data(), source.size());
+    h2 = fnv1a(h2, source.data(), source.size());
+    h2 = fnv1a(h2, arch.data(), arch.size());
+    for (auto const &o : options) h2 = fnv1a(h2, o.data(), o.size() + 1);
+    char const *li = std::getenv("BBFFT_CUDA_JIT_LINEINFO");
+    if (li && *li == '0') h2 = fnv1a(h2, "nolineinfo", 10);
+    char name[64];
+    std::snprintf(name, sizeof(name), "/%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+    return std::string(dir) + name;
+}
+} // namespace
+
+static std::vector<std::uint8_t> nvrtc_compile_uncached(std::string const &source, std::string const &arch,
+                                                        std::vector<std::string> const &extra_options);
+
 std::vector<std::uint8_t> nvrtc_compile(std::string const &source, std::string const &arch,
                                         std::vector<std::string> const &extra_options) {
+    const std::string path = disk_cache_path(source, arch, extra_options);
+    if (!path.empty()) {
+        std::ifstream f(path, std::ios::binary);
+        if (f) {
+            std::vector<std::uint8_t> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            if (!bin.empty()) return bin;
+        }
+    }
+    auto bin = nvrtc_compile_uncached(source, arch, extra_options);
+    if (!path.empty()) {
+        // write-then-rename so that concurrent processes never see a partial file; a cache that
+        // cannot be written is not an error
+        const std::string tmp = path + ".tmp" + std::to_string(static_cast<long long>(::getpid())) + "_" +
+                                std::to_string(reinterpret_cast<std::uintptr_t>(&bin));
+        std::ofstream f(tmp, std::ios::binary);
+        if (f) {
+            f.write(reinterpret_cast<char const *>(bin.data()), std::streamsize(bin.size()));
+            f.close();
+            if (!f || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+        }
+    }
+    return bin;
+}
+
+static std::vector<std::uint8_t> nvrtc_compile_uncached(std::string const &source, std::string const &arch,
+                                                        std::vector<std::string> const &extra_options) {
     auto &rt = nvrtc();
     void *prog = nullptr;
     const char *headers[] = {kernel_header_text()};
@@ -81,8 +150,11 @@ std::vector<std::uint8_t> nvrtc_compile(std::string const &source, std::string c
     if (rc != 0) {
         throw error(std::string("nvrtcCreateProgram failed: ") + rt.error_string(rc), rc);
     }
-    std::vector<std::string> opts = {"--gpu-architecture=" + arch, "-std=c++17", "-lineinfo",
-                                     "-default-device"};
+    std::vector<std::string> opts = {"--gpu-architecture=" + arch, "-std=c++17", "-default-device"};
+    // line tables let ncu map SASS back to bbfft_kernels.cuh; BBFFT_CUDA_JIT_LINEINFO=0 drops them
+    // (5x smaller cubins for the persistent cache, identical code)
+    char const *li = std::getenv("BBFFT_CUDA_JIT_LINEINFO");
+    if (!(li && *li == '0')) opts.push_back("-lineinfo");
     for (auto const &o : extra_options) opts.push_back(o);
     std::vector<const char *> copts;
     for (auto const &o : opts) copts.push_back(o.c_str());

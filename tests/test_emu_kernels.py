@@ -54,7 +54,7 @@ def test_c2c_emulated_nonpacked_strides(pkg, oracle):
     assert _run_c2c(pkg, oracle, M, N, K, 8, 1, istride=s, ostride=[1, M, M * N]) < TOL[8] * 0.1
 
 
-def _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=False):
+def _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=False, tune=""):
     from common import addressed_mask, real_problem
     rng = np.random.default_rng(ttype * 7919 + M * 131 + N * 17 + K)
     d = -1 if ttype == 1 else 1
@@ -67,13 +67,13 @@ def _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=False):
         raw[: x.nbytes] = x.view(np.uint8)
         ref = raw.copy()
         oracle.dft(ocfg, ref)
-        emu.run(cfg, raw, None)
+        emu.run(cfg, raw, None, tune)
         got, want = raw.view(odt)[:nout], ref.view(odt)[:nout]
     else:
         want = np.zeros(nout, odt)
         oracle.dft(ocfg, x, want)
         got = np.zeros(nout, odt)
-        emu.run(cfg, x, got)
+        emu.run(cfg, x, got, tune)
     mask = addressed_mask(M, N // 2 + 1 if ttype == 1 else N, K, ost, nout)
     if not inplace:
         assert np.all(got[~mask] == 0), "kernel wrote outside the addressed elements"
@@ -92,6 +92,33 @@ def test_real_emulated_kernel_vs_oracle(pkg, oracle, fp, ttype, M, N, K):
         if inplace and d["inplace_unsupported"]:
             continue
         assert _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=(ttype == 2)) < TOL[fp] * 0.1
+
+
+@pytest.mark.parametrize("ttype", [1, 2])
+@pytest.mark.parametrize("M,N,K,tune", [(16, 64, 3, "RF=0"), (16, 64, 3, "RF=1"), (1, 256, 5, "RF=1,LD=0,ST=0"), (1, 256, 5, "RF=0,LD=0,ST=0"),
+                                        (16, 27, 3, "RF=0"), (4, 105, 4, "RF=0,R=3x5x7"), (4, 105, 5, "RF=1,R=7x5x3,T=11"),
+                                        (8, 500, 2, "RF=1,R=25x10,T=13"), (8, 500, 2, "RF=1,R=10x25,T=6"), (16, 48, 3, "RF=1,ML=8")])
+def test_real_fused_and_separate_pass_emulated(pkg, oracle, ttype, M, N, K, tune):
+    """The real pre/post pass fused into the first/last stage (RF=1, mirrored sub-FFT pairs) and run
+    as a separate pass over shared memory (RF=0) are both planner choices; the tuner explores them."""
+    for fp in (4, 8):
+        for inplace in (False, True):
+            d = pkg.describe(pkg.make_config(1, [M, N, K], fp, -1 if ttype == 1 else 1, ttype, inplace=inplace), tune)
+            assert ("_rf1" in d["identifier"]) == ("RF=1" in tune)
+            if inplace and d["inplace_unsupported"]:
+                continue
+            assert _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=(ttype == 2), tune=tune) < TOL[fp] * 0.1
+
+
+def test_real_inplace_lanes_cover_m(pkg):
+    # strides that let the spectrum overlay the real rows make the lanes cover M (M <= 32), so the
+    # cases the reference runs in place (test/r2c.cpp, golden c2r_f64_M16_N48_K3_ip) are supported
+    for fp in (4, 8):
+        for M in (2, 3, 16, 17, 32):
+            for ttype, d in ((pkg.R2C, pkg.FORWARD), (pkg.C2R, pkg.BACKWARD)):
+                for N in (48, 27, 441):
+                    desc = pkg.describe(pkg.make_config(1, [M, N, 6], fp, d, ttype, inplace=True))
+                    assert not desc["inplace_unsupported"], (fp, M, N, desc["identifier"])
 
 
 def test_real_inplace_unsupported_flag(pkg):
