@@ -33,8 +33,10 @@ M_BATCH = 16
 TENSOR_BYTES = 1 << 30
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2 GiB = 2147483648 algorithmic bytes)
 # from the ncu --set full capture of the N=64 fp32 kernel of this sweep
-NCU_TRAFFIC_PER_LAUNCH = 1073814000 + 1022701000
-NCU_TRAFFIC_SOURCE = "profiles/r01b_ncu_full_summary.txt (c2c f32 M=16 N=64: read 1.0738 GB + write 1.0227 GB; the tail of the output is still dirty in L2 when the kernel ends)"
+NCU_TRAFFIC_PER_LAUNCH = 1073752000 + 1025303000
+NCU_TRAFFIC_SOURCE = ("profiles/r01e_ncu_full_summary.txt (c2c f32 M=16 N=64: read 1.073752 GB + write 1.025303 GB; "
+                      "N=500 f32: 1.073751 + 1.030455 GB; N=441 f64: 1.073669 + 1.025061 GB; the tail of the output "
+                      "is still dirty in L2 when the kernel ends)")
 
 
 def sweep_sizes():
@@ -232,6 +234,10 @@ def other_configs(peak):
             for inplace in (False, True):
                 bc.bench_real_1d(rows, nm, 4, 1, 256, 1 << 20, stream, ttype, inplace)
         bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64", 8, (64, 64, 64), 64, stream)
+        bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64, one launch per step", 8, (64, 64, 64), 64, stream,
+                    env={"BBFFT_CUDA_ND_CHAIN": "0"})
+        bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64, multi-pass (reference decomposition)", 8, (64, 64, 64), 64, stream,
+                    env={"BBFFT_CUDA_ND_CHAIN": "0", "BBFFT_CUDA_ND_FUSE": "0"})
         bc.bench_nd(rows, "C4 2d c2c f32 128^2 K=64 (L2 resident)", 4, (128, 128), 64, stream)
         bc.bench_nd(rows, "C4 2d shape at 1 GiB", 4, (128, 128), 8192, stream)
         bc.bench_c2c_1d(rows, "C5 c2c f32 M=16 N=256 identity load/store callbacks", 4, 16, 256, (1 << 30) // (16 * 256 * 8),

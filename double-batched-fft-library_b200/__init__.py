@@ -19,6 +19,7 @@ from .capi import (  # noqa: F401
     compile_to_cubin,
     default_strides,
     describe,
+    describe_chain,
     generate_kernels,
     kernel_header,
     lib,

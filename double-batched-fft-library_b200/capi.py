@@ -61,6 +61,26 @@ class KernelDesc(C.Structure):
     ]
 
 
+class ChainDesc(C.Structure):
+    _fields_ = [
+        ("identifier", C.c_void_p),
+        ("source", C.c_void_p),
+        ("twiddle", C.POINTER(C.c_double)),
+        ("twiddle_len", C.c_size_t),
+        ("threads", C.c_int),
+        ("smem_bytes", C.c_size_t),
+        ("min_blocks", C.c_int),
+        ("fp", C.c_int),
+        ("n_steps", C.c_int),
+        ("step_tile", C.c_int * 3),
+        ("per_k", C.c_uint64 * 3),
+        ("mult", C.c_uint64 * 3),
+        ("step_M", C.c_uint64 * 3),
+        ("tw_offset", C.c_int * 3),
+        ("uses_tmp", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -97,6 +117,9 @@ def lib():
         l.bbfft_cuda_describe.argtypes = [C.POINTER(Config), C.c_char_p, C.POINTER(KernelDesc)]
         l.bbfft_cuda_desc_free.argtypes = [C.POINTER(KernelDesc)]
         l.bbfft_cuda_desc_free.restype = None
+        l.bbfft_cuda_describe_chain.argtypes = [C.POINTER(Config), C.POINTER(ChainDesc)]
+        l.bbfft_cuda_chain_desc_free.argtypes = [C.POINTER(ChainDesc)]
+        l.bbfft_cuda_chain_desc_free.restype = None
         l.bbfft_cuda_generate_kernels.argtypes = [C.POINTER(Config), C.c_size_t, C.POINTER(C.c_void_p),
                                                   C.POINTER(C.c_void_p)]
         l.bbfft_cuda_compile.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -189,6 +212,27 @@ def describe(cfg, tune=""):
         )
     finally:
         lib().bbfft_cuda_desc_free(C.byref(d))
+    return out
+
+
+def describe_chain(cfg):
+    """Device-free planning of a 2d/3d configuration as one persistent chain kernel (raises
+    BadConfiguration when its steps cannot be chained)."""
+    import numpy as np
+    d = ChainDesc()
+    _check(lib().bbfft_cuda_describe_chain(C.byref(cfg), C.byref(d)))
+    try:
+        n = int(d.n_steps)
+        out = dict(
+            identifier=C.string_at(d.identifier).decode(),
+            source=C.string_at(d.source).decode(),
+            twiddle=np.ctypeslib.as_array(d.twiddle, shape=(max(1, d.twiddle_len),))[: d.twiddle_len].copy(),
+            threads=int(d.threads), smem_bytes=int(d.smem_bytes), min_blocks=int(d.min_blocks), fp=int(d.fp),
+            n_steps=n, step_tile=list(d.step_tile)[:n], per_k=list(d.per_k)[:n], mult=list(d.mult)[:n],
+            step_M=list(d.step_M)[:n], tw_offset=list(d.tw_offset)[:n], uses_tmp=bool(d.uses_tmp),
+        )
+    finally:
+        lib().bbfft_cuda_chain_desc_free(C.byref(d))
     return out
 
 

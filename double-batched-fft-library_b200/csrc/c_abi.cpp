@@ -226,7 +226,9 @@ int bbfft_cuda_plan_execute_host(bbfft_cuda_plan_t plan, const void *host_in, si
         // c+1 overlaps the kernel and the D2H copy of slab c (PCIe is full duplex).
         std::uint64_t chunks = 1;
         if (K > 1 && isl > 0 && osl > 0 && K * isl <= in_bytes + isl && (in_bytes + out_bytes) > (32u << 20)) {
-            chunks = std::min<std::uint64_t>(8, K / 2);
+            // slabs of >= 16 MiB, at most 16: the un-overlapped head (first H2D) and tail (last D2H)
+            // of the synchronous call shrink with the slab size
+            chunks = std::min<std::uint64_t>(std::min<std::uint64_t>(16, K / 2), std::max<std::size_t>(2, in_bytes >> 24));
         }
         if (chunks <= 1) {
             BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, host_in, in_bytes, cudaMemcpyHostToDevice, s));
@@ -320,6 +322,57 @@ int bbfft_cuda_describe(const bbfft_cuda_config *cfg, const char *tune, bbfft_cu
         desc->load_staged = kp.p.load_staged;
         desc->store_staged = kp.p.store_staged;
     });
+}
+
+int bbfft_cuda_describe_chain(const bbfft_cuda_config *cfg, bbfft_cuda_chain_desc *desc) {
+    return guarded([&] {
+        std::memset(desc, 0, sizeof(*desc));
+        auto c = to_cpp(*cfg);
+        if (c.dim < 2) throw bad_configuration("bbfft_cuda_describe_chain handles 2d and 3d configurations");
+        auto steps = cuda::nd_decompose(c, cuda::device_props{});
+        std::vector<cuda::chain_step_problem> probs;
+        for (auto const &s : steps) {
+            cuda::chain_step_problem q;
+            q.tile = s.fused;
+            q.mult = s.mult;
+            if (s.fused) {
+                q.t = s.tile;
+            } else {
+                q.p = cuda::to_problem(s.pass);
+            }
+            probs.push_back(q);
+        }
+        cuda::chain_plan_t cp;
+        if (!cuda::plan_chain(probs, cuda::device_props{}, cp)) {
+            throw bad_configuration("bbfft_cuda_describe_chain: the steps of this configuration cannot be chained");
+        }
+        desc->identifier = dup_string(cp.identifier);
+        desc->source = dup_string(cp.source);
+        desc->twiddle_len = cp.twiddle.size();
+        desc->twiddle = static_cast<double *>(std::malloc(sizeof(double) * std::max<std::size_t>(1, cp.twiddle.size())));
+        std::memcpy(desc->twiddle, cp.twiddle.data(), sizeof(double) * cp.twiddle.size());
+        desc->threads = cp.threads;
+        desc->smem_bytes = cp.smem_bytes;
+        desc->min_blocks = cp.min_blocks;
+        desc->fp = static_cast<int>(c.fp);
+        desc->n_steps = int(cp.steps.size());
+        for (std::size_t d = 0; d < cp.steps.size(); ++d) {
+            desc->step_tile[d] = cp.steps[d].tile;
+            desc->per_k[d] = cp.steps[d].per_k;
+            desc->mult[d] = probs[d].mult;
+            desc->step_M[d] = cp.steps[d].tile ? cp.steps[d].tp.p.M : cp.steps[d].kp.p.M;
+            desc->tw_offset[d] = cp.steps[d].tw_offset;
+        }
+        desc->uses_tmp = c.type == transform_type::c2r;
+    });
+}
+
+void bbfft_cuda_chain_desc_free(bbfft_cuda_chain_desc *desc) {
+    if (!desc) return;
+    std::free(desc->identifier);
+    std::free(desc->source);
+    std::free(desc->twiddle);
+    std::memset(desc, 0, sizeof(*desc));
 }
 
 void bbfft_cuda_desc_free(bbfft_cuda_kernel_desc *desc) {

@@ -117,6 +117,20 @@ BBK_DEV cx<double> ldg_cx(const cx<double> *p) {
 }
 #endif
 
+// L2-only load of a tensor element: for data another SM wrote during the same launch (chain)
+#ifdef BBFFT_EMU
+template <class T> BBK_DEV cx<T> ldcg_cx(const cx<T> *p) { return *p; }
+#else
+BBK_DEV cx<float> ldcg_cx(const cx<float> *p) {
+    float2 r = __ldcg(reinterpret_cast<const float2 *>(p));
+    return cx<float>{r.x, r.y};
+}
+BBK_DEV cx<double> ldcg_cx(const cx<double> *p) {
+    double2 r = __ldcg(reinterpret_cast<const double2 *>(p));
+    return cx<double>{r.x, r.y};
+}
+#endif
+
 template <int I> struct ic {
     static constexpr int value = I;
 };
@@ -877,7 +891,8 @@ BBK_DEV void coop_copy(E *sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, i
     }
 }
 
-template <class C> BBK_DEV void fft1d(args const &a) {
+// the work of CTA `bid` of the 1d kernel's grid
+template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
     using T = typename C::real_t;
     using G = geom<C>;
     cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
@@ -886,7 +901,6 @@ template <class C> BBK_DEV void fft1d(args const &a) {
     const int t = (tid / C::ML) % C::T;
     const int bh = tid / (C::ML * C::T);
     const int b = l0 + C::ML * bh;
-    const u64 bid = BBK_BID();
     u64 m, k, m0, k0;
     if constexpr (C::KLANES) {
         m0 = 0;
@@ -1123,6 +1137,8 @@ template <class C> BBK_DEV void fft1d(args const &a) {
     }
 }
 
+template <class C> BBK_DEV void fft1d(args const &a) { fft1d_cta<C>(a, BBK_BID()); }
+
 // ------------------------------------------------------------------------------------------
 // Fused 2d c2c transform ("tile kernel").  One CTA owns one M x N1 x N2 tile -- contiguous in
 // global memory for the default layout, element (m, n1, n2) at m + M*n1 + M*N1*n2 -- keeps it in
@@ -1241,16 +1257,141 @@ BBK_DEV void tile_pass(args const &a, cx<typename C::real_t> *sm, u64 gbase, int
     }
 }
 
-template <class C> BBK_DEV void fft2d_tile(args const &a) {
+template <class C> BBK_DEV void fft2d_tile_cta(args const &a, const u64 tile) {
     using T = typename C::real_t;
     cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
     const int tid = BBK_TID();
-    const u64 tile = BBK_BID();
-    if (tile >= a.K) return;
     const u64 gbase = tile * u64(C::TILE_STRIDE);
     tile_pass<C, typename C::PA, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, gbase, tid);
     BBK_SYNC();
     tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL>(a, sm, gbase, tid);
+}
+
+template <class C> BBK_DEV void fft2d_tile(args const &a) {
+    const u64 tile = BBK_BID();
+    if (tile >= a.K) return;
+    fft2d_tile_cta<C>(a, tile);
+}
+
+// ------------------------------------------------------------------------------------------
+// Chained nd transform: ONE persistent launch runs every step of a 2d/3d decomposition (fused
+// tile kernel and/or double-batched 1d passes; reference nd_fft: one launch per mode,
+// src/common/algorithm/nd_fft.hpp:140-152).  The outer batch index k is the slowest index of
+// every step, so step d of slab k depends only on step d-1 of slab k.  Work items (step, k, CTA
+// of that step's grid inside slab k) are ordered in pipeline slots -- slot s holds step d of
+// k-block s-d -- and dealt round-robin to the resident CTAs.  A block of slabs is a few MiB, so
+// what step d-1 wrote is still in the 126 MB L2 when step d reads it one slot later: HBM sees
+// one read and one write of the tensor instead of one round trip per step, without the drain at
+// every kernel boundary that made host-side L2 blocking lose (profiles/r01c_nd_block.txt).
+//
+// Dependencies: done[d*K + k] counts finished CTAs of step d, slab k (monotonic over launches:
+// launch number `epoch` waits for epoch * PER_K).  A waiting item only ever waits for items that
+// precede it in the item order; every CTA walks its items in that order and the whole grid is
+// resident (grid <= SMs * occupancy, chosen by the host), so the earliest unfinished item is
+// always running: no deadlock.  Steps d > 0 read what other SMs wrote during this launch, so
+// their stubs load with ld.global.cg (L2 only; L1 is not coherent).
+// ------------------------------------------------------------------------------------------
+struct chain_args {
+    args step[3];
+    u64 *done;  // [steps][K]
+    u64 epoch;  // 1, 2, 3, ... one per launch of this plan
+    u64 K;      // outer batch (slabs)
+    u64 kblock; // slabs per pipeline block
+};
+
+enum : int { STEP_FFT1D = 0, STEP_TILE = 1 };
+
+#ifdef BBFFT_EMU
+#define BBK_NCTAS() (::bbfft_emu::grid_dim())
+BBK_DEV void chain_wait(u64 const *p, u64 target) {
+    if (*p < target) ::bbfft_emu::fail(); // one emulated CTA runs the items in order: never waits
+}
+BBK_DEV void chain_signal(u64 *p) { *p += 1; }
+#else
+#define BBK_NCTAS() (u64(gridDim.x))
+BBK_DEV void chain_wait(u64 const *p, u64 target) {
+    const volatile u64 *vp = p;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (*vp < target) {
+        __nanosleep(100);
+        if ((++spins & 1023u) == 0) {
+            // a dependency that does not arrive within seconds is a bug: fault instead of hanging the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 8000000000ll) __trap();
+        }
+    }
+    __threadfence();
+}
+BBK_DEV void chain_signal(u64 *p) {
+    __threadfence();
+    atomicAdd(reinterpret_cast<unsigned long long *>(p), 1ull);
+}
+#endif
+
+template <class S> BBK_DEV void chain_run_step(args const &a, u64 bid) {
+    if constexpr (S::KIND == STEP_TILE) {
+        fft2d_tile_cta<typename S::C>(a, bid);
+    } else {
+        fft1d_cta<typename S::C>(a, bid);
+    }
+}
+
+// S0, S1, S2: step descriptors {C, KIND, PER_K = CTAs of the step per slab}; NS of them are used.
+template <int NS, class S0, class S1, class S2> BBK_DEV void chain(chain_args const &ca) {
+    static_assert(NS == 2 || NS == 3, "a chain has two or three steps");
+    // (a function, not an array: a dynamically indexed array would live in local memory)
+    auto per_k_of = [](int d) { return d == 0 ? u64(S0::PER_K) : (d == 1 ? u64(S1::PER_K) : u64(S2::PER_K)); };
+    const u64 nblk = (ca.K + ca.kblock - 1) / ca.kblock;
+    const u64 nslots = nblk + NS - 1;
+    auto blk_slabs = [&](u64 j) { return (j + 1) * ca.kblock <= ca.K ? ca.kblock : ca.K - j * ca.kblock; };
+    auto slot_items = [&](u64 sl) {
+        u64 n = 0;
+        for (int d = 0; d < NS; ++d) {
+            if (sl >= u64(d) && sl - d < nblk) n += blk_slabs(sl - d) * per_k_of(d);
+        }
+        return n;
+    };
+    const int tid = BBK_TID();
+    u64 slot = 0, base = 0, cur = slot_items(0);
+    for (u64 it = BBK_BID();; it += BBK_NCTAS()) {
+        while (slot < nslots && it >= base + cur) {
+            base += cur;
+            ++slot;
+            cur = slot < nslots ? slot_items(slot) : 0;
+        }
+        if (slot >= nslots) break;
+        u64 r = it - base;
+        int d = 0;
+        u64 j = 0;
+        for (; d < NS; ++d) {
+            if (slot >= u64(d) && slot - d < nblk) {
+                const u64 n = blk_slabs(slot - d) * per_k_of(d);
+                if (r < n) {
+                    j = slot - d;
+                    break;
+                }
+                r -= n;
+            }
+        }
+        const u64 pk = per_k_of(d);
+        const u64 k = j * ca.kblock + r / pk;
+        const u64 bid = k * pk + r % pk;
+        if (d > 0 && tid == 0) chain_wait(ca.done + u64(d - 1) * ca.K + k, ca.epoch * per_k_of(d - 1));
+        BBK_SYNC(); // dependency visible to the CTA; shared memory of the previous item is free
+        if (d == 0) {
+            chain_run_step<S0>(ca.step[0], bid);
+        } else if (d == 1) {
+            chain_run_step<S1>(ca.step[1], bid);
+        } else {
+            if constexpr (NS == 3) chain_run_step<S2>(ca.step[2], bid);
+        }
+        if (d < NS - 1) {
+            BBK_SYNC(); // every store of the CTA is issued before the release below
+            if (tid == 0) chain_signal(ca.done + u64(d) * ca.K + k);
+        }
+    }
 }
 
 } // namespace bbk

@@ -350,9 +350,76 @@ std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &
     return steps;
 }
 
+// All steps in one persistent launch (bbk::chain) when they can share a CTA shape.
+// BBFFT_CUDA_ND_CHAIN=0 keeps one launch per step; BBFFT_CUDA_ND_CHAIN_KBLOCK / _CTAS override the
+// slabs per pipeline block and the resident CTAs per SM.
+bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
+    char const *env = std::getenv("BBFFT_CUDA_ND_CHAIN");
+    if ((env && *env == '0') || steps.size() < 2 || K_ == 0) return false;
+    if (char const *blk = std::getenv("BBFFT_CUDA_ND_BLOCK_BYTES")) {
+        if (std::strtoull(blk, nullptr, 10) > 0) return false; // host-side L2 blocking was asked for explicitly
+    }
+    std::vector<chain_step_problem> probs;
+    std::size_t fp = 4;
+    for (auto const &s : steps) {
+        chain_step_problem c;
+        c.tile = s.fused;
+        c.mult = s.mult;
+        if (s.fused) {
+            c.t = s.tile;
+            fp = std::size_t(s.tile.fp);
+            step_in_bytes_.push_back(std::size_t(s.tile.tile_stride) * 2 * fp * s.mult);
+            step_out_bytes_.push_back(step_in_bytes_.back());
+        } else {
+            c.p = to_problem(s.pass);
+            fp = std::size_t(c.p.fp);
+            step_in_bytes_.push_back(std::size_t(c.p.is2) * (c.p.type == 1 ? 1 : 2) * fp * s.mult);
+            step_out_bytes_.push_back(std::size_t(c.p.os2) * (c.p.type == 2 ? 1 : 2) * fp * s.mult);
+        }
+        probs.push_back(c);
+    }
+    if (!plan_chain(probs, api_.props(), chain_)) return false;
+    jit_cache_key key{chain_.identifier, api_.device_id()};
+    if (cache) chain_module_ = cache->get(key);
+    if (!chain_module_) chain_module_ = builtin_module(chain_.identifier, api_.device());
+    if (!chain_module_) {
+        chain_module_ = api_.build_module(chain_.source);
+        if (cache) cache->store(key, chain_module_);
+    }
+    chain_kernel_ = api_.create_kernel(chain_module_.get(), chain_.identifier, chain_.smem_bytes);
+    // every CTA of the persistent grid must be resident: the runtime's occupancy figure, or (when it
+    // cannot be queried) the planner's own -- __maxnreg__ and the shared-memory check guarantee it
+    int per_sm = api_.max_active_ctas_per_sm(chain_kernel_, chain_.threads, chain_.smem_bytes);
+    if (per_sm < 1) per_sm = chain_.min_blocks;
+    if (char const *e = std::getenv("BBFFT_CUDA_ND_CHAIN_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
+    chain_grid_ = std::uint64_t(per_sm) * std::uint64_t(api_.props().sm_count);
+    // slabs per pipeline block: about two waves of the step with the fewest CTAs per slab, but at most
+    // 16 MiB of tensor (three blocks are in flight: well inside the L2)
+    std::uint64_t min_per_k = ~0ull;
+    std::size_t slab_bytes = 1;
+    for (std::size_t d = 0; d < chain_.steps.size(); ++d) {
+        min_per_k = std::min(min_per_k, chain_.steps[d].per_k);
+        slab_bytes = std::max(slab_bytes, std::max(step_in_bytes_[d], step_out_bytes_[d]));
+    }
+    chain_kblock_ = std::max<std::uint64_t>(1, (2 * chain_grid_ + min_per_k - 1) / min_per_k);
+    chain_kblock_ = std::min<std::uint64_t>(chain_kblock_, std::max<std::uint64_t>(1, (16u << 20) / slab_bytes));
+    if (char const *e = std::getenv("BBFFT_CUDA_ND_CHAIN_KBLOCK")) chain_kblock_ = std::max(1ull, std::strtoull(e, nullptr, 10));
+    chain_tw_ = api_.create_twiddle_table(chain_.twiddle, int(fp));
+    chain_done_ = api_.create_device_buffer(sizeof(std::uint64_t) * chain_.steps.size() * K_);
+    BBFFT_CUDA_CHECK(cudaMemsetAsync(chain_done_, 0, sizeof(std::uint64_t) * chain_.steps.size() * K_, api_.stream()));
+    BBFFT_CUDA_CHECK(cudaStreamSynchronize(api_.stream()));
+    return true;
+}
+
 nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::move(a)), dim_(cfg.dim) {
     K_ = cfg.shape[dim_ + 1];
-    for (auto const &s : nd_decompose(cfg, api_.props())) {
+    auto steps = nd_decompose(cfg, api_.props());
+    chained_ = try_chain(steps, cache);
+    for (auto const &s : steps) {
+        if (chained_) {
+            mult_.push_back(s.mult);
+            continue;
+        }
         if (s.fused) {
             plans_.push_back(std::make_shared<fft2d_plan>(s.tile, api_, cache));
         } else {
@@ -386,18 +453,43 @@ nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::
     }
 }
 
-nd_plan::~nd_plan() { api_.release_buffer(tmp_); }
+nd_plan::~nd_plan() {
+    api_.release_buffer(tmp_);
+    api_.release_buffer(chain_tw_);
+    api_.release_buffer(chain_done_);
+}
 
 unsigned nd_plan::launches_per_execute() const {
+    if (chained_) return 1;
     std::uint64_t blocks = kblock_ ? (K_ + kblock_ - 1) / kblock_ : 1;
     return unsigned(plans_.size() * std::max<std::uint64_t>(1, blocks));
 }
 
 void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
     void *tmp = tmp_ ? tmp_ : out;
-    const std::size_t n = plans_.size();
+    const std::size_t n = chained_ ? chain_.steps.size() : plans_.size();
     auto src = [&](std::size_t d) { return d == 0 ? in : static_cast<void const *>(tmp); };
     auto dst = [&](std::size_t d) { return d + 1 == n ? out : tmp; };
+    if (chained_) {
+        chain_kernel_args ca = {};
+        const std::size_t esz = 2 * std::size_t(chain_.steps[0].tile ? chain_.steps[0].tp.p.fp : chain_.steps[0].kp.p.fp);
+        for (std::size_t d = 0; d < n; ++d) {
+            auto const &sp = chain_.steps[d];
+            ca.step[d].in = src(d);
+            ca.step[d].out = dst(d);
+            ca.step[d].tw = static_cast<char const *>(chain_tw_) + std::size_t(sp.tw_offset) * esz;
+            ca.step[d].K = mult_[d] * K_;
+            ca.step[d].M = sp.tile ? sp.tp.p.M : sp.kp.p.M;
+        }
+        ca.done = static_cast<unsigned long long *>(chain_done_);
+        ca.epoch = ++chain_epoch_;
+        ca.K = K_;
+        ca.kblock = chain_kblock_;
+        std::uint64_t items = 0;
+        for (auto const &sp : chain_.steps) items += sp.per_k * K_;
+        api_.launch_kernel_raw(chain_kernel_, std::min(chain_grid_, items), chain_.threads, chain_.smem_bytes, &ca, stream);
+        return;
+    }
     if (kblock_ == 0 || kblock_ >= K_) {
         for (std::size_t d = 0; d < n; ++d) plans_[d]->enqueue(src(d), dst(d), stream);
         return;
@@ -441,7 +533,7 @@ std::vector<std::string> generate_fft_kernels(std::ostream &os, std::vector<conf
     cuda::device_props dev;
     if (info.max_work_group_size) dev.max_threads_per_block = int(info.max_work_group_size);
     if (info.local_memory_size) dev.max_smem_per_block = info.local_memory_size;
-    std::vector<std::string> names;
+    std::vector<std::string> names, chain_stubs;
     auto emit = [&](configuration const &c1) {
         auto kp = cuda::plan_kernel_1d(cuda::to_problem(c1), dev, std::string());
         for (auto const &n : names) {
@@ -455,7 +547,41 @@ std::vector<std::string> generate_fft_kernels(std::ostream &os, std::vector<conf
             emit(cfg);
         } else {
             // same decomposition as nd_plan, without a device
-            for (auto const &st : cuda::nd_decompose(cfg, dev)) {
+            auto steps = cuda::nd_decompose(cfg, dev);
+            {
+                // the persistent chain kernel nd_plan launches when the steps can share a CTA shape
+                std::vector<cuda::chain_step_problem> probs;
+                for (auto const &st : steps) {
+                    cuda::chain_step_problem q;
+                    q.tile = st.fused;
+                    q.mult = st.mult;
+                    if (st.fused) {
+                        q.t = st.tile;
+                    } else {
+                        q.p = cuda::to_problem(st.pass);
+                    }
+                    probs.push_back(q);
+                }
+                cuda::chain_plan_t cp;
+                bool seen = false;
+                if (cuda::plan_chain(probs, dev, cp)) {
+                    for (auto const &n : names) seen = seen || n == cp.identifier;
+                    if (!seen) {
+                        for (auto const &sp : cp.steps) {
+                            std::string const &sid = sp.tile ? sp.tp.identifier : sp.kp.identifier;
+                            bool have = false;
+                            for (auto const &n : chain_stubs) have = have || n == sid;
+                            if (!have) {
+                                chain_stubs.push_back(sid);
+                                os << (sp.tile ? sp.tp.source : sp.kp.source) << "\n";
+                            }
+                        }
+                        names.push_back(cp.identifier);
+                        os << cp.entry_source << "\n";
+                    }
+                }
+            }
+            for (auto const &st : steps) {
                 if (!st.fused) {
                     emit(st.pass);
                     continue;

@@ -120,9 +120,11 @@ class nd_plan : public plan_base {
     unsigned launches_per_execute() const override;
     std::vector<std::shared_ptr<plan_base>> const &passes() const { return plans_; }
     void kernel_names(std::vector<std::string> &names) const override {
+        if (chained_) names.push_back(chain_.identifier);
         for (auto const &q : plans_) q->kernel_names(names);
     }
     std::uint64_t k_block() const { return kblock_; }
+    bool chained() const { return chained_; }
 
   private:
     api api_;
@@ -131,6 +133,15 @@ class nd_plan : public plan_base {
     std::vector<std::uint64_t> mult_; // slices of pass d per outer k
     std::uint64_t K_ = 0, kblock_ = 0; // outer batch and its L2 block (in k)
     void *tmp_ = nullptr;
+    // chained execution: all steps in one persistent launch (bbk::chain)
+    bool try_chain(std::vector<nd_step> const &steps, jit_cache *cache);
+    bool chained_ = false;
+    chain_plan_t chain_;
+    std::vector<std::size_t> step_in_bytes_, step_out_bytes_; // bytes of one slab as step d sees it
+    shared_handle<module_handle_t> chain_module_;
+    cudaKernel_t chain_kernel_ = nullptr;
+    void *chain_tw_ = nullptr, *chain_done_ = nullptr;
+    std::uint64_t chain_epoch_ = 0, chain_kblock_ = 1, chain_grid_ = 0;
 };
 
 // kernel from the built-in ahead-of-time bundle, or an empty handle

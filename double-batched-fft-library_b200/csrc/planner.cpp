@@ -439,20 +439,17 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
                 if (!tune.count(kv.first)) tune[kv.first] = kv.second;
             }
         }
-        // a measured entry for exactly this transform wins over the c2c entry of its length
-        char const *w = (use && !sp) ? wisdom_lookup(prob.fp, int(clen)) : nullptr;
+        // The c2c table is for c2c only.  Real transforms have their own measured entries
+        // (wisdom_real.inc, every seven-smooth N >= 27); a real size without one runs the heuristic,
+        // which is what the tuner measured as its default -- a c2c entry of the same complex length
+        // was tuned for a different live-register set (measured: profiles/r01e_real_sweep.jsonl,
+        // r2c f32 N=441 at 0.29 of peak with the inherited 21x21 entry).
+        (void)clen;
+        char const *w = (use && !sp && prob.type == 0) ? wisdom_lookup(prob.fp, int(prob.N)) : nullptr;
         if (w && *w) {
             auto wt = parse_tune(w);
             int wml = wt.count("ML") ? std::atoi(wt["ML"].c_str()) : 0;
-            // a real transform inherits the c2c entry only if one of its radices is small enough
-            // for the mirrored stage, and never its register cap (its live set differs)
-            bool real_ok = true;
-            if (prob.type != 0 && wt.count("R")) {
-                auto rr = parse_radices(wt["R"]);
-                real_ok = rr.size() < 2 || *std::min_element(rr.begin(), rr.end()) <= (prob.fp == 4 ? 16 : 8);
-                wt.erase("MB");
-            }
-            if (real_ok && wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
+            if (wml > 0 && prob.M >= std::uint64_t(wml) && prob.M % wml == 0) {
                 for (auto const &kv : wt) {
                     if (!tune.count(kv.first)) tune[kv.first] = kv.second;
                 }
@@ -682,6 +679,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
     p.max_regs = reg_cap(p.threads, p.min_blocks);
 
+    p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
     // real in-place transforms need one CTA to own every m of a k slice, like the reference
     // (src/base/generator/small_batch_fft.cpp:38, factor2_slm_fft.cpp:63)
     plan.inplace_unsupported = real && !p.klanes && std::uint64_t(p.ML) < prob.M;
@@ -707,6 +705,7 @@ std::string make_identifier(kernel_params const &p) {
        << int(p.load_staged) << "_st" << int(p.store_staged) << "_pk" << p.PADK << "_row" << p.ROW
        << "_is" << p.is1 << "_" << p.is2 << "_os" << p.os1 << "_" << p.os2;
     if (p.mode != k_c2c) os << "_pl" << int(p.pair_load) << "_ps" << int(p.pair_store) << "_rf" << int(p.real_fused);
+    if (p.chained) os << "_ch";
     if (!p.cb_load.empty()) os << "_" << p.cb_load;
     if (!p.cb_store.empty()) os << "_" << p.cb_store;
     std::string s = os.str();
@@ -895,7 +894,12 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     // (reference: callback_accessor, src/base/generator/tensor_accessor.cpp:34-55)
     const bool in_real = p.mode == k_r2c_half || p.mode == k_r2c_double;
     const bool out_real = p.mode == k_c2r_half || p.mode == k_c2r_double;
-    if (p.cb_load.empty()) {
+    if (p.cb_load.empty() && p.chained) {
+        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
+              "        return bbk::ldcg_cx(reinterpret_cast<const bbk::cx<real_t> *>(in) + off);\n    }\n";
+        os << "    static BBK_DEV real_t ldr(const void *in, bbk::u64 off) {\n"
+              "        return reinterpret_cast<const real_t *>(in)[off];\n    }\n";
+    } else if (p.cb_load.empty()) {
         os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
               "        return reinterpret_cast<const bbk::cx<real_t> *>(in)[off];\n    }\n";
         os << "    static BBK_DEV real_t ldr(const void *in, bbk::u64 off) {\n"
@@ -928,8 +932,10 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     os << "    static constexpr bool HAS_CALLBACKS = "
        << ((p.cb_load.empty() && p.cb_store.empty()) ? "false" : "true") << ";\n";
     os << "};\n} // namespace stub_" << identifier << "\n";
-    os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") "
-       << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
+    if (!p.chained) {
+        os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") "
+           << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
+    }
     os << "#ifdef BBFFT_OCL_COMPAT\n#undef float2\n#undef double2\n#undef BBFFT_OCL_COMPAT\n#endif\n";
     return os.str();
 }
@@ -1126,6 +1132,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     }
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
     p.max_regs = reg_cap(p.threads, p.min_blocks);
+    p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
 
     // identifier
     {
@@ -1136,6 +1143,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         os << "_rb";
         for (int s = 0; s < p.b.L; ++s) os << (s ? "x" : "") << p.b.radix[s];
         os << "_th" << p.threads << "_mb" << p.min_blocks << "_pk" << p.PADK << "_ts" << p.tile_stride;
+        if (p.chained) os << "_ch";
         plan.identifier = os.str();
     }
     // twiddles: pass A stages, then pass B stages (same construction as the 1d table)
@@ -1195,16 +1203,149 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         os << "struct C {\n    using real_t = " << real << ";\n    using PA = PassA;\n    using PB = PassB;\n";
         os << "    static constexpr int DIR = " << p.dir << ", THREADS = " << p.threads << ", PADK = " << p.PADK
            << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull;\n";
-        os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
-              "        return reinterpret_cast<const bbk::cx<real_t> *>(in)[off];\n    }\n";
+        if (p.chained) {
+            os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
+                  "        return bbk::ldcg_cx(reinterpret_cast<const bbk::cx<real_t> *>(in) + off);\n    }\n";
+        } else {
+            os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
+                  "        return reinterpret_cast<const bbk::cx<real_t> *>(in)[off];\n    }\n";
+        }
         os << "    static BBK_DEV void st(void *out, bbk::u64 off, bbk::cx<real_t> v) {\n"
               "        reinterpret_cast<bbk::cx<real_t> *>(out)[off] = v;\n    }\n";
         os << "};\n} // namespace stub_" << plan.identifier << "\n";
-        os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") " << plan.identifier
-           << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
+        if (!p.chained) {
+            os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") " << plan.identifier
+               << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
+        }
         plan.source = os.str();
     }
     return plan;
+}
+
+// ------------------------------------------------------------------------------------------
+// chain: all steps of an nd decomposition in one persistent kernel (bbk::chain)
+// ------------------------------------------------------------------------------------------
+bool plan_chain(std::vector<chain_step_problem> const &steps, device_props const &dev, chain_plan_t &out) {
+    if (steps.size() < 2 || steps.size() > 3) return false;
+    out = chain_plan_t{};
+    // common CTA shape: the tile kernel's thread count when there is one, else 256
+    int threads = 256;
+    for (auto const &s : steps) {
+        if (s.tile) {
+            tile_plan tp = plan_kernel_2d(s.t, dev, "CH=1");
+            threads = tp.p.threads;
+        }
+    }
+    for (auto const &s : steps) {
+        chain_step_plan sp;
+        sp.tile = s.tile;
+        if (s.tile) {
+            sp.tp = plan_kernel_2d(s.t, dev, "CH=1,TH=" + std::to_string(threads));
+            if (sp.tp.p.threads != threads || s.mult == 0) return false;
+            sp.per_k = s.mult; // one CTA per tile
+        } else {
+            // r2c reads its real input around C::ld (pair loads): fine for the first step only, whose
+            // input no other SM writes during the launch
+            if (s.p.type == 1 && !out.steps.empty()) return false;
+            // the step's own plan gives radices, threads per transform and the preferred lanes; lanes
+            // and batch are re-chosen so that the CTA has the common thread count and never
+            // straddles two slabs
+            kernel_plan def = plan_kernel_1d(s.p, dev, "");
+            if (def.p.klanes || def.p.L < 2) return false;
+            std::uint64_t kunits = s.mult; // k slices of the step per slab
+            if (def.p.mode == k_r2c_double || def.p.mode == k_c2r_double) {
+                if (kunits % 2) return false;
+                kunits /= 2;
+            }
+            std::vector<int> ml_pref;
+            if (s.p.M == 1) {
+                ml_pref = {1};
+            } else {
+                for (int c = def.p.ML; c <= 32; c *= 2) ml_pref.push_back(c);
+                for (int c = def.p.ML / 2; c >= 2; c /= 2) ml_pref.push_back(c);
+            }
+            // threads per transform: the plan's own, else more (fewer sub-FFTs per thread) up to
+            // one sub-FFT of the smallest radix per thread
+            int min_r = def.p.radix[0];
+            for (int i = 1; i < def.p.L; ++i) min_r = std::min(min_r, def.p.radix[i]);
+            int T = 0, ml = 0, bh = 0;
+            for (int tc = def.p.T; tc <= def.p.N / min_r && ml == 0; ++tc) {
+                if (threads % tc != 0) continue;
+                const int lanes_total = threads / tc; // ML * BH
+                for (int c : ml_pref) {
+                    if (lanes_total % c != 0) continue;
+                    const int b = lanes_total / c;
+                    if (kunits % std::uint64_t(b) != 0) continue;
+                    // real in-place capable layouts keep every m of a slice in one CTA
+                    if (s.p.type != 0 && def.p.ML >= int(s.p.M) && c < int(s.p.M)) continue;
+                    T = tc;
+                    ml = c;
+                    bh = b;
+                    break;
+                }
+            }
+            if (ml == 0) return false;
+            std::ostringstream tn;
+            tn << "CH=1,R=";
+            for (int i = 0; i < def.p.L; ++i) tn << (i ? "x" : "") << def.p.radix[i];
+            tn << ",T=" << T << ",ML=" << ml << ",BH=" << bh;
+            sp.kp = plan_kernel_1d(s.p, dev, tn.str());
+            if (sp.kp.p.threads != threads || sp.kp.p.klanes || sp.kp.p.ML != ml || sp.kp.p.BH != bh) return false;
+            if (sp.kp.inplace_unsupported && !def.inplace_unsupported) return false;
+            sp.per_k = (kunits / bh) * ((s.p.M + ml - 1) / ml);
+        }
+        out.steps.push_back(std::move(sp));
+    }
+    out.threads = threads;
+    out.min_blocks = 8;
+    for (auto const &sp : out.steps) {
+        out.smem_bytes = std::max(out.smem_bytes, sp.tile ? sp.tp.p.smem_bytes : sp.kp.p.smem_bytes);
+        out.min_blocks = std::min(out.min_blocks, sp.tile ? sp.tp.p.min_blocks : sp.kp.p.min_blocks);
+    }
+    while (out.min_blocks > 1 && ((out.smem_bytes + 1024) * std::size_t(out.min_blocks) > dev.smem_per_sm ||
+                                  threads * out.min_blocks > 2048)) {
+        --out.min_blocks;
+    }
+    if (out.smem_bytes > dev.max_smem_per_block) return false;
+    out.max_regs = reg_cap(threads, out.min_blocks);
+    std::ostringstream id;
+    id << "bbfft_chain" << out.steps.size() << "_mb" << out.min_blocks;
+    std::ostringstream stubs, os;
+    stubs << "// generated by bbfft-cuda planner -- do not edit\n#include \"bbfft_kernels.cuh\"\n";
+    std::uint64_t h = 1469598103934665603ull;
+    std::set<std::string> emitted;
+    for (auto &sp : out.steps) {
+        std::string const &sid = sp.tile ? sp.tp.identifier : sp.kp.identifier;
+        for (char c : sid) h = (h ^ static_cast<unsigned char>(c)) * 1099511628211ull;
+        h = (h ^ sp.per_k) * 1099511628211ull;
+        if (emitted.insert(sid).second) stubs << (sp.tile ? sp.tp.source : sp.kp.source);
+        auto const &tw = sp.tile ? sp.tp.twiddle : sp.kp.twiddle;
+        sp.tw_offset = int(out.twiddle.size() / 2);
+        out.twiddle.insert(out.twiddle.end(), tw.begin(), tw.end());
+    }
+    {
+        // the step identifiers are long: the chain's name carries a hash of them
+        char buf[32];
+        std::snprintf(buf, sizeof(buf), "_%016llx", static_cast<unsigned long long>(h));
+        auto const &first = out.steps.front();
+        id << (first.tile ? "_t" : "_p") << "_f" << ((first.tile ? first.tp.p.fp : first.kp.p.fp) * 8) << "_th"
+           << threads << buf;
+    }
+    out.identifier = id.str();
+    os << "namespace chain_" << out.identifier << " {\n";
+    for (std::size_t i = 0; i < 3; ++i) {
+        auto const &sp = out.steps[std::min(i, out.steps.size() - 1)];
+        os << "struct S" << i << " {\n    using C = stub_" << (sp.tile ? sp.tp.identifier : sp.kp.identifier)
+           << "::C;\n    static constexpr int KIND = " << (sp.tile ? 1 : 0) << ";\n    static constexpr bbk::u64 PER_K = "
+           << sp.per_k << "ull;\n};\n";
+    }
+    os << "} // namespace chain_" << out.identifier << "\n";
+    os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << out.max_regs << ") " << out.identifier
+       << "(bbk::chain_args ca) {\n    bbk::chain<" << out.steps.size() << ", chain_" << out.identifier << "::S0, chain_"
+       << out.identifier << "::S1, chain_" << out.identifier << "::S2>(ca);\n}\n";
+    out.entry_source = os.str();
+    out.source = stubs.str() + out.entry_source;
+    return true;
 }
 
 } // namespace bbfft::cuda

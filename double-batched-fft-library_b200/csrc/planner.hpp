@@ -46,6 +46,7 @@ struct kernel_params {
     bool klanes = false, load_staged = false, store_staged = false;
     bool pair_load = false, pair_store = false; // real side is read/written as aligned complex words
     bool real_fused = false; // real pre/post pass fused into the first/last stage (mirrored sub-FFT pairs)
+    bool chained = false;    // stub is a step of a chain kernel: no entry point, L2-only (ld.global.cg) loads
     std::uint64_t M = 1;
     std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1;
     int LL = 1, PADK = 0, ROW = 1;
@@ -73,7 +74,7 @@ struct kernel_plan {
     bool inplace_unsupported = false;
 };
 
-// Tuning overrides, "key=value,key=value" (keys: R=8x8, T, ML, BH, MB, LD, ST, RF, PADK, ROW, KL).
+// Tuning overrides, "key=value,key=value" (keys: R=8x8, T, ML, BH, MB, LD, ST, RF, PADK, ROW, KL, CH).
 // Used by the auto-tuner and the tests; empty string = heuristics.
 kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
                            std::string const &tune = std::string());
@@ -101,6 +102,7 @@ struct tile_params {
     tile_pass_params a, b; // axis n1, axis n2
     int threads = 256, PADK = 0, min_blocks = 1, max_regs = 255;
     std::size_t smem_bytes = 0;
+    bool chained = false; // see kernel_params::chained
 };
 
 struct tile_plan {
@@ -115,6 +117,31 @@ bool tile_fusable(problem_2d const &prob, device_props const &dev);
 // Tuning overrides: RA=8x16, RB=16x8, TH=<threads>, PADK, MB.
 tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev,
                          std::string const &tune = std::string());
+
+// ---- chained nd kernel (bbk::chain): every step of a 2d/3d decomposition in ONE persistent launch ----
+struct chain_step_problem {
+    bool tile = false;
+    problem_2d t;           // tile == true
+    problem_1d p;           // tile == false
+    std::uint64_t mult = 1; // slices of the step per outer k (slab)
+};
+struct chain_step_plan {
+    bool tile = false;
+    tile_plan tp;
+    kernel_plan kp;
+    std::uint64_t per_k = 1; // CTAs of the step's grid per slab
+    int tw_offset = 0;       // first complex element of the step's twiddles in the chain's table
+};
+struct chain_plan_t {
+    std::vector<chain_step_plan> steps;
+    std::string identifier, source;
+    std::string entry_source;    // the part of `source` after the steps' stubs (chain traits + entry point)
+    std::vector<double> twiddle; // all steps, interleaved re,im
+    int threads = 0, min_blocks = 1, max_regs = 255;
+    std::size_t smem_bytes = 0;
+};
+// Returns false when the steps cannot share one CTA shape (the caller then launches them one by one).
+bool plan_chain(std::vector<chain_step_problem> const &steps, device_props const &dev, chain_plan_t &out);
 
 // integer helpers (pinned by tests; semantics of reference src/base/prime_factorization.cpp)
 std::vector<int> prime_factors(int n);

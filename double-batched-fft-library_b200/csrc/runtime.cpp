@@ -364,6 +364,24 @@ void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::si
                                       dim3(unsigned(threads)), params, smem_bytes, stream));
 }
 
+void api::launch_kernel_raw(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
+                            void *param, cudaStream_t stream) const {
+    if (grid == 0) return;
+    void *params[] = {param};
+    BBFFT_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void *>(k), dim3(unsigned(grid)),
+                                      dim3(unsigned(threads)), params, smem_bytes, stream));
+}
+
+int api::max_active_ctas_per_sm(cudaKernel_t k, int threads, std::size_t smem_bytes) const {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, reinterpret_cast<const void *>(k), threads, smem_bytes) !=
+        cudaSuccess) {
+        (void)cudaGetLastError(); // not every runtime accepts a cudaKernel_t here: the caller falls back
+        return 0;
+    }
+    return n;
+}
+
 void *api::create_device_buffer(std::size_t bytes) const {
     void *p = nullptr;
     BBFFT_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));

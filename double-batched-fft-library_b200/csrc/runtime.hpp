@@ -28,6 +28,12 @@ struct kernel_args { // must match bbk::args
     long long is1, is2, os1, os2;
 };
 
+struct chain_kernel_args { // must match bbk::chain_args
+    kernel_args step[3];
+    unsigned long long *done;
+    unsigned long long epoch, K, kblock;
+};
+
 class api {
   public:
     explicit api(cudaStream_t stream, int device = -1);
@@ -44,6 +50,11 @@ class api {
     cudaKernel_t create_kernel(module_handle_t mod, std::string const &name, std::size_t smem_bytes) const;
     void launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
                        kernel_args const &args, cudaStream_t stream) const;
+    // launch with an arbitrary by-value parameter block (chain kernels: bbk::chain_args)
+    void launch_kernel_raw(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
+                           void *param, cudaStream_t stream) const;
+    // resident CTAs per SM of `k` with this CTA shape
+    int max_active_ctas_per_sm(cudaKernel_t k, int threads, std::size_t smem_bytes) const;
     void *create_device_buffer(std::size_t bytes) const;
     void release_buffer(void *ptr) const;
     // narrow the double table to `fp` bytes per real and upload it

@@ -106,6 +106,29 @@ typedef struct bbfft_cuda_kernel_desc {
 } bbfft_cuda_kernel_desc;
 int bbfft_cuda_describe(const bbfft_cuda_config *cfg, const char *tune, bbfft_cuda_kernel_desc *desc);
 void bbfft_cuda_desc_free(bbfft_cuda_kernel_desc *desc);
+
+/* Device-free planning of a 2d/3d configuration as ONE persistent "chain" kernel (all steps of the
+ * reference's nd_fft, src/common/algorithm/nd_fft.hpp:140-152, in one launch with L2-resident
+ * intermediates).  Fails with status 2 when the steps cannot be chained. */
+typedef struct bbfft_cuda_chain_desc {
+    char *identifier;
+    char *source;
+    double *twiddle;     /* all steps, interleaved re, im */
+    size_t twiddle_len;  /* number of doubles */
+    int threads;
+    size_t smem_bytes;
+    int min_blocks;
+    int fp;
+    int n_steps;
+    int step_tile[3];      /* 1 = fused 2d tile step, 0 = double-batched 1d pass */
+    uint64_t per_k[3];     /* CTAs of the step per outer k */
+    uint64_t mult[3];      /* k slices (tiles) of the step per outer k */
+    uint64_t step_M[3];
+    int tw_offset[3];      /* first complex element of the step's twiddles */
+    int uses_tmp;          /* the plan routes intermediates through a temporary (c2r) */
+} bbfft_cuda_chain_desc;
+int bbfft_cuda_describe_chain(const bbfft_cuda_config *cfg, bbfft_cuda_chain_desc *desc);
+void bbfft_cuda_chain_desc_free(bbfft_cuda_chain_desc *desc);
 /* All kernels (1d..3d) of a list of configurations as one translation unit; *source is
  * malloc'ed, *names is a malloc'ed '\n'-separated list. */
 int bbfft_cuda_generate_kernels(const bbfft_cuda_config *cfgs, size_t n, char **source, char **names);

@@ -15,6 +15,8 @@ struct thread_ctx {
     unsigned char *smem;
     void (*yield)(thread_ctx *);
 };
+extern unsigned long long grid_size; // CTAs of the emulated launch (persistent kernels stride by it)
+extern int failed;                   // set by device code that would hang or trap on the GPU
 extern thread_local thread_ctx *current;
 inline void syncthreads() {
     thread_ctx *c = current;
@@ -24,5 +26,7 @@ inline void syncthreads() {
 inline int thread_idx() { return current->tid; }
 inline unsigned long long block_idx() { return current->bid; }
 inline unsigned char *shared_mem() { return current->smem; }
+inline unsigned long long grid_dim() { return grid_size; }
+inline void fail() { failed = 1; }
 } // namespace bbfft_emu
 #endif

@@ -39,7 +39,8 @@ def _compile(desc):
         with open(stub, "w") as f:
             f.write(desc["source"])
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        cmd = [cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DBBFFT_EMU",
+        extra = ["-DBBFFT_EMU_CHAIN"] if desc["source"].startswith("#define BBFFT_EMU_CHAIN") else []
+        cmd = [cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DBBFFT_EMU"] + extra + [
                "-DBBFFT_EMU_KERNEL=" + desc["identifier"], "-I" + _HERE, "-I" + _KERNELS, "-include",
                os.path.join(_HERE, "cuda_emu.hpp"), stub, os.path.join(_HERE, "emu_runner.cpp"), "-o",
                so + ".tmp"]
@@ -64,3 +65,34 @@ def run(cfg, inp, out=None, tune=""):
     if rc != 0:
         raise RuntimeError("emulated kernel failed (rc=%d): divergent barriers" % rc)
     return out, desc
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [("step", Args * 3), ("done", C.c_void_p), ("epoch", C.c_ulonglong), ("K", C.c_ulonglong),
+                ("kblock", C.c_ulonglong)]
+
+
+def run_chain(cfg, inp, out, kblock=2, epochs=1):
+    """Execute the persistent chain kernel of a 2d/3d `cfg` with ONE emulated CTA (it walks all work
+    items in dependency order, so a wait that would spin on the GPU is a test failure)."""
+    desc = pkg.describe_chain(cfg)
+    desc["source"] = "#define BBFFT_EMU_CHAIN 1\n" + desc["source"]
+    lib = _compile(desc)
+    lib.emu_launch.argtypes = [C.POINTER(ChainArgs), C.c_ulonglong, C.c_int, C.c_ulong]
+    rdt = np.float32 if desc["fp"] == 4 else np.float64
+    tw = desc["twiddle"].astype(rdt)
+    K = cfg.shape[cfg.dim + 1]
+    n = desc["n_steps"]
+    done = np.zeros(n * K, dtype=np.uint64)
+    assert not desc["uses_tmp"], "emulated chains route intermediates through `out`"
+    for epoch in range(1, epochs + 1):
+        a = ChainArgs()
+        for d in range(n):
+            src = inp if d == 0 else out
+            a.step[d] = Args(src.ctypes.data, out.ctypes.data, tw.ctypes.data + desc["tw_offset"][d] * 2 * tw.itemsize,
+                             desc["mult"][d] * K, desc["step_M"][d], 0, 0, 0, 0)
+        a.done, a.epoch, a.K, a.kblock = done.ctypes.data, epoch, K, kblock
+        rc = lib.emu_launch(C.byref(a), 1, desc["threads"], desc["smem_bytes"])
+        if rc != 0:
+            raise RuntimeError("emulated chain kernel failed (rc=%d)" % rc)
+    return out, desc, done

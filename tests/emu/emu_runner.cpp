@@ -9,10 +9,18 @@
 #include <ucontext.h>
 #include <vector>
 
-extern "C" void BBFFT_EMU_KERNEL(bbk::args a);
+// chain kernels (-DBBFFT_EMU_CHAIN) take bbk::chain_args, everything else bbk::args
+#ifdef BBFFT_EMU_CHAIN
+typedef bbk::chain_args emu_args_t;
+#else
+typedef bbk::args emu_args_t;
+#endif
+extern "C" void BBFFT_EMU_KERNEL(emu_args_t a);
 
 namespace bbfft_emu {
 thread_local thread_ctx *current = nullptr;
+unsigned long long grid_size = 1;
+int failed = 0;
 }
 
 namespace {
@@ -25,7 +33,7 @@ struct fiber {
 };
 thread_local ucontext_t sched_uc;
 thread_local fiber *running = nullptr;
-thread_local bbk::args *launch_args = nullptr;
+thread_local emu_args_t *launch_args = nullptr;
 
 void yield_to_sched(bbfft_emu::thread_ctx *) {
     fiber *f = running;
@@ -40,8 +48,10 @@ void fiber_main() {
 }
 } // namespace
 
-extern "C" int emu_launch(bbk::args *a, unsigned long long grid, int threads, unsigned long smem_bytes) {
+extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, unsigned long smem_bytes) {
     launch_args = a;
+    bbfft_emu::grid_size = grid;
+    bbfft_emu::failed = 0;
     std::vector<fiber> fibers(threads);
     for (auto &f : fibers) {
         f.stack = static_cast<char *>(std::malloc(stack_bytes));
@@ -79,5 +89,5 @@ extern "C" int emu_launch(bbk::args *a, unsigned long long grid, int threads, un
         }
     }
     for (auto &f : fibers) std::free(f.stack);
-    return 0;
+    return bbfft_emu::failed ? 3 : 0;
 }

@@ -200,3 +200,42 @@ def test_c2c_2d_emulated_tile_kernel_vs_oracle(pkg, oracle, fp, M, N1, N2, K, tu
     z = x.copy()
     emu.run(cfg, z, None, tune)
     assert np.array_equal(z, y)
+
+
+# ---- chained nd kernel (bbk::chain): all steps of a 2d/3d plan in one persistent launch ----------
+@pytest.mark.parametrize("desc,fp,shape_np,kind,kblock,epochs", [
+    ("dcfo32x32x32*3", 8, (3, 32, 32, 32, 1), "c2c", 2, 1),      # fused tile step + 1d pass
+    ("dcfo32x32x32*5", 8, (5, 32, 32, 32, 1), "c2c", 2, 2),      # second launch: counters keep counting
+    ("srfo128x64*6", 4, (6, 64, 128, 1), "r2c", 4, 1),            # r2c pass + c2c pass with M' = 65
+    ("scfo1024x64*3", 4, (3, 64, 1024, 1), "c2c", 1, 1),          # two 1d passes, M = 1 first
+])
+def test_chain_kernel_emulated(pkg, desc, fp, shape_np, kind, kblock, epochs):
+    """One emulated CTA walks every work item of the chain in its dependency order (a wait that
+    would spin on the GPU fails the run): index maps, slab/step decoding, counters."""
+    cfg = pkg.parse_descriptor(desc)
+    rng = np.random.default_rng(1)
+    cdt = np.complex64 if fp == 4 else np.complex128
+    axes = tuple(range(1, len(shape_np) - 1))
+    if kind == "r2c":
+        x = rng.standard_normal(shape_np).astype(np.float32 if fp == 4 else np.float64)
+        ref = np.fft.rfftn(x.astype(np.float64), axes=axes)
+    else:
+        x = (rng.standard_normal(shape_np) + 1j * rng.standard_normal(shape_np)).astype(cdt)
+        ref = np.fft.fftn(x.astype(np.complex128), axes=axes)
+    y = np.zeros(ref.shape, cdt)
+    _, d, done = emu.run_chain(cfg, x.reshape(-1), y.reshape(-1), kblock=kblock, epochs=epochs)
+    assert d["identifier"].startswith("bbfft_chain")
+    assert rel_l2(y, ref) < TOL[fp] * 0.1
+    K = shape_np[0]
+    # every step but the last signals once per CTA and launch
+    for s in range(d["n_steps"] - 1):
+        assert np.all(done[s * K:(s + 1) * K] == epochs * d["per_k"][s])
+
+
+def test_chain_planning_falls_back(pkg):
+    # steps that cannot share one CTA shape are launched one by one: no chain description
+    for desc in ("scfo3.6x5x4*2", "scfo128x128*64"):
+        with pytest.raises(pkg.BadConfiguration):
+            pkg.describe_chain(pkg.parse_descriptor(desc))
+    d = pkg.describe_chain(pkg.parse_descriptor("dcfo64x64x64*64"))
+    assert d["step_tile"] == [1, 0] and d["per_k"] == [64, 128] and d["threads"] == 256

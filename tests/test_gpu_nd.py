@@ -3,7 +3,9 @@ through the C ABI, against numpy's float64 fftn / rfftn / irfftn on the same ten
 import numpy as np
 import pytest
 
-from common import TOL, cdtype, rdtype, rel_l2
+from common import C2R, R2C, TOL, cdtype, rdtype, rel_l2
+
+C2C = 0
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -124,17 +126,20 @@ def test_c2c_nd_fused_equals_multipass_and_l2_blocking(pkg, monkeypatch, fp, M, 
     xd = torch.from_numpy(x).cuda()
     per_k = x.nbytes // K
     results = {}
-    for name, env in (("fused", {}), ("multipass", {"BBFFT_CUDA_ND_FUSE": "0"}),
+    nochain = {"BBFFT_CUDA_ND_CHAIN": "0"}
+    for name, env in (("default", {}), ("fused", nochain), ("multipass", dict(nochain, BBFFT_CUDA_ND_FUSE="0")),
                       ("fused-blocked", {"BBFFT_CUDA_ND_BLOCK_BYTES": str(2 * per_k)}),
-                      ("multipass-unblocked", {"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_BLOCK_BYTES": "0"})):
-        for k in ("BBFFT_CUDA_ND_FUSE", "BBFFT_CUDA_ND_BLOCK_BYTES"):
+                      ("multipass-unblocked", dict(nochain, BBFFT_CUDA_ND_FUSE="0", BBFFT_CUDA_ND_BLOCK_BYTES="0")),
+                      ("multipass-chained", {"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN_KBLOCK": "1"})):
+        for k in ("BBFFT_CUDA_ND_FUSE", "BBFFT_CUDA_ND_BLOCK_BYTES", "BBFFT_CUDA_ND_CHAIN", "BBFFT_CUDA_ND_CHAIN_KBLOCK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, pkg.FORWARD, pkg.C2C, inplace=False)
         plan = pkg.Plan(cfg, stream=_stream())
         yd = torch.zeros_like(xd)
-        plan.execute(xd, yd)
+        for _ in range(3):  # chained plans count launches (epochs): repeated executes must agree
+            plan.execute(xd, yd)
         torch.cuda.synchronize()
         results[name] = (yd.cpu().numpy(), plan.kernel_names, plan.launches_per_execute)
         plan.close()
@@ -144,6 +149,88 @@ def test_c2c_nd_fused_equals_multipass_and_l2_blocking(pkg, monkeypatch, fp, M, 
     assert results["fused-blocked"][2] == (dim - 1) * ((K + 1) // 2)
     for name, (y, names, _) in results.items():
         assert rel_l2(y, ref) < TOL[fp], (name, names)
+    # one persistent launch for all steps where they can share a CTA shape (bbk::chain); it only
+    # changes the schedule, never the arithmetic
+    for name in ("default", "multipass-chained"):
+        if results[name][1][0].startswith("bbfft_chain"):
+            assert results[name][2] == 1 and len(results[name][1]) == 1
+    if dim == 3 and M == 1 and Ns[0] >= 32:
+        assert results["default"][1][0].startswith("bbfft_chain2"), results["default"][1]
+    assert np.array_equal(results["default"][0], results["fused"][0])
+    assert np.array_equal(results["multipass-chained"][0], results["multipass"][0])
     # blocking only changes the launch schedule, never the arithmetic
     assert np.array_equal(results["fused"][0], results["fused-blocked"][0])
     assert np.array_equal(results["multipass"][0], results["multipass-unblocked"][0])
+
+
+@pytest.mark.parametrize("fp,ttype,Ns,K", [(4, R2C, (128, 64), 6), (4, C2R, (128, 64), 6), (8, R2C, (256, 48), 5),
+                                          (4, C2C, (1024, 64), 3), (8, C2C, (512, 512), 2), (4, C2C, (256, 128, 64), 2),
+                                          (4, R2C, (128, 64, 32), 2), (8, C2R, (128, 64, 64), 2)])
+def test_nd_chain_matches_one_launch_per_step(pkg, monkeypatch, fp, ttype, Ns, K):
+    """Chains of double-batched 1d passes (no fused tile: r2c/c2r, tiles beyond shared memory, three
+    passes): same bits as one launch per step, and right against numpy."""
+    dim = len(Ns)
+    rng = np.random.default_rng(5 + sum(Ns))
+    sig_shape = (K,) + tuple(reversed(Ns)) + (1,)
+    xr = rng.standard_normal(sig_shape)
+    if ttype == C2C:
+        x = (xr + 1j * rng.standard_normal(sig_shape)).astype(cdtype(fp))
+        ref = np.fft.fftn(x.astype(np.complex128), axes=_axes(dim))
+        nout, odt, d = x.size, cdtype(fp), pkg.FORWARD
+    elif ttype == R2C:
+        x = xr.astype(rdtype(fp))
+        ref = np.fft.fftn(np.fft.rfft(x.astype(np.float64), axis=dim), axes=_axes(dim)[:-1]) if dim > 1 else None
+        nout, odt, d = ref.size, cdtype(fp), pkg.FORWARD
+    else:
+        spec = np.fft.fftn(np.fft.rfft(xr, axis=dim), axes=_axes(dim)[:-1])
+        x = spec.astype(cdtype(fp))
+        ref = xr * np.prod(Ns)
+        nout, odt, d = ref.size, rdtype(fp), pkg.BACKWARD
+    outs = {}
+    for name, env in (("chain", {}), ("steps", {"BBFFT_CUDA_ND_CHAIN": "0"})):
+        monkeypatch.delenv("BBFFT_CUDA_ND_CHAIN", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        cfg = pkg.make_config(dim, [1] + list(Ns) + [K], fp, d, ttype, inplace=False)
+        plan = pkg.Plan(cfg, stream=_stream())
+        xd = torch.from_numpy(x).cuda()
+        yd = torch.zeros(nout, dtype=torch.from_numpy(np.zeros(1, odt)).dtype, device="cuda")
+        for _ in range(2):
+            plan.execute(xd, yd)
+        torch.cuda.synchronize()
+        outs[name] = (yd.cpu().numpy(), plan.kernel_names, plan.launches_per_execute)
+        plan.close()
+    assert outs["chain"][1][0].startswith("bbfft_chain") and outs["chain"][2] == 1, outs["chain"][1]
+    assert outs["steps"][2] == dim
+    assert rel_l2(outs["chain"][0].reshape(ref.shape), ref) < TOL[fp]
+    assert np.array_equal(outs["chain"][0], outs["steps"][0])
+
+
+def test_config4_3d_chain_full_size(pkg, monkeypatch):
+    """BASELINE config 4 at full size (3d c2c fp64 64^3, K=64, 256 MiB): the chained plan equals the
+    two-launch plan bit for bit, in place as well, over repeated executes."""
+    K = 64
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(4)
+    x = torch.randn(K * 64 * 64 * 64, 2, dtype=torch.float64, device="cuda", generator=gen)
+    outs = {}
+    for name, env in (("chain", {}), ("steps", {"BBFFT_CUDA_ND_CHAIN": "0"})):
+        monkeypatch.delenv("BBFFT_CUDA_ND_CHAIN", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        cfg = pkg.make_config(3, [1, 64, 64, 64, K], 8, pkg.FORWARD, pkg.C2C, inplace=False)
+        plan = pkg.Plan(cfg, stream=_stream())
+        y = torch.zeros_like(x)
+        for _ in range(3):
+            plan.execute(x, y)
+        z = x.clone()
+        plan.execute(z)
+        torch.cuda.synchronize()
+        outs[name] = (y, z, plan.kernel_names)
+        plan.close()
+    assert outs["chain"][2][0].startswith("bbfft_chain2")
+    assert torch.equal(outs["chain"][0], outs["steps"][0])
+    assert torch.equal(outs["chain"][1], outs["steps"][0])
+    want = torch.fft.fftn(torch.view_as_complex(x).view(K, 64, 64, 64)[:2], dim=(1, 2, 3))
+    got = torch.view_as_complex(outs["chain"][0]).view(K, 64, 64, 64)[:2]
+    assert float((got - want).norm() / want.norm()) < TOL[8]

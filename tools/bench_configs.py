@@ -156,10 +156,20 @@ def bench_real_1d(rows, name, fp, M, N, K, stream, ttype, inplace, cufft=True):
     plan.close()
 
 
-def bench_nd(rows, name, fp, dims, K, stream, tune=""):
+def bench_nd(rows, name, fp, dims, K, stream, tune="", env=None):
+    """`env`: BBFFT_CUDA_ND_* switches in force while the plan is created (chain / fuse / blocking)."""
     shape = [1] + list(dims) + [K]
     cfg = pkg.make_config(len(dims), shape, fp, pkg.FORWARD, pkg.C2C, inplace=False)
-    plan = pkg.Plan(cfg, stream=stream, tune=tune)
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        plan = pkg.Plan(cfg, stream=stream, tune=tune)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     tdims = [K] + list(reversed(dims))
     x = torch.view_as_complex(torch.rand(*tdims, 2, dtype=rdt(fp), device="cuda"))
     y = torch.empty_like(x)
@@ -210,8 +220,18 @@ def main():
                 bench_real_1d(rows, nm, 4, 16, 256, 1 << 16, stream, ttype, inplace)
     if "c4" in which:
         bench_nd(rows, "C4-3d", 8, (64, 64, 64), 64, stream)
+        bench_nd(rows, "C4-3d-two-launches", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "0"})
+        bench_nd(rows, "C4-3d-multipass", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "0", "BBFFT_CUDA_ND_FUSE": "0"})
+        for kb in (1, 2, 8):
+            bench_nd(rows, "C4-3d-chain-kblock%d" % kb, 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN_KBLOCK": str(kb)})
+        bench_nd(rows, "C4-3d-chain-1cta", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN_CTAS": "1"})
+        bench_nd(rows, "C4-3d-f32-256^3", 4, (256, 256, 256), 8, stream)
+        bench_nd(rows, "C4-3d-f32-256^3-steps", 4, (256, 256, 256), 8, stream, env={"BBFFT_CUDA_ND_CHAIN": "0"})
         bench_nd(rows, "C4-2d", 4, (128, 128), 64, stream)
         bench_nd(rows, "C4-2d-big", 4, (128, 128), 8192, stream)
+        bench_nd(rows, "C4-2d-big-chained-passes", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
+        bench_nd(rows, "C4-2d-big-two-launches", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN": "0"})
+        bench_nd(rows, "C4-2d-chained-passes", 4, (128, 128), 64, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
     if "c5" in which:
         for n in (64, 256):
             k = (1 << 30) // (16 * n * 8)

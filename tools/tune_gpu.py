@@ -149,7 +149,8 @@ def main():
         for path in args.cands.split(","):
             for key, tunes in json.load(open(path)).items():
                 t, fp, n = key.split(",")
-                todo[(t, int(fp), int(n))] = tunes
+                have = todo.setdefault((t, int(fp), int(n)), [])
+                have += [x for x in tunes if x not in have]
     else:
         pairs = []
         if args.from_csv:

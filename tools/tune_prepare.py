@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--from-csv", default="", help="per-size CSV of bench.py: only the c2c (fp, N) below --below")
     ap.add_argument("--below", type=float, default=0.9)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--only-wisdom", action="store_true", help="compile only the current wisdom entries of the sizes")
     ap.add_argument("--max-stack", type=int, default=64, help="drop candidates that spill more than this many bytes")
     ap.add_argument("--out", default=os.path.join(ROOT, "tune_cache"))
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 8)
@@ -47,6 +48,12 @@ def main():
     import tune_gpu
 
     sizes = [int(s) for s in args.sizes.split(",")] if args.sizes else [n for n in aot.smooth_sizes() if n >= args.minN]
+    wisdom = {}
+    import re as _re
+    for line in open(os.path.join(ROOT, "double-batched-fft-library_b200", "csrc", "wisdom.inc")):
+        m = _re.match(r'\{(\d+), (\d+), "([^"]*)"\}', line)
+        if m:
+            wisdom[(int(m.group(1)), int(m.group(2)))] = m.group(3)
     jobs = []
     pairs = [(int(f), n) for f in args.fp.split(",") for n in sizes]
     if args.from_csv:
@@ -56,7 +63,11 @@ def main():
         for fp, n in pairs:
             if True:
                 cfg, K = tune_gpu.make_cfg(pkg, ttype, fp, n, args.M, args.bytes)
-                for tune in tune_gpu.candidates(n, fp, args.M, ttype):
+                tunes = [] if args.only_wisdom else tune_gpu.candidates(n, fp, args.M, ttype)
+                # the entry the library uses today competes as well, so a re-tune can never regress
+                if ttype == "c2c" and (fp, n) in wisdom and wisdom[(fp, n)] not in tunes:
+                    tunes.append(wisdom[(fp, n)])
+                for tune in tunes:
                     jobs.append((ttype, fp, n, cfg, tune))
     print("%d candidates to compile" % len(jobs), flush=True)
 
