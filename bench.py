@@ -234,10 +234,10 @@ def other_configs(peak):
             for inplace in (False, True):
                 bc.bench_real_1d(rows, nm, 4, 1, 256, 1 << 20, stream, ttype, inplace)
         bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64", 8, (64, 64, 64), 64, stream)
-        bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64, one launch per step", 8, (64, 64, 64), 64, stream,
-                    env={"BBFFT_CUDA_ND_CHAIN": "0"})
+        bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64, chained (one persistent launch, L2-resident intermediate)", 8,
+                    (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "1"})
         bc.bench_nd(rows, "C4 3d c2c f64 64^3 K=64, multi-pass (reference decomposition)", 8, (64, 64, 64), 64, stream,
-                    env={"BBFFT_CUDA_ND_CHAIN": "0", "BBFFT_CUDA_ND_FUSE": "0"})
+                    env={"BBFFT_CUDA_ND_FUSE": "0"})
         bc.bench_nd(rows, "C4 2d c2c f32 128^2 K=64 (L2 resident)", 4, (128, 128), 64, stream)
         bc.bench_nd(rows, "C4 2d shape at 1 GiB", 4, (128, 128), 8192, stream)
         bc.bench_c2c_1d(rows, "C5 c2c f32 M=16 N=256 identity load/store callbacks", 4, 16, 256, (1 << 30) // (16 * 256 * 8),

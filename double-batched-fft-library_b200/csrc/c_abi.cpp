@@ -186,8 +186,15 @@ int bbfft_cuda_plan_create_tuned(bbfft_cuda_plan_t *plan, const bbfft_cuda_confi
         auto p = std::make_unique<bbfft_cuda_plan_s>();
         p->device = a.device();
         jit_cache *jc = cache ? &cache->cache : nullptr;
-        if (tune && *tune) {
-            if (c.dim != 1) throw bad_configuration("tuned plans are 1d only");
+        if (tune && *tune && c.dim == 2) {
+            // 2d: overrides of the fused tile kernel (RA, RB, TH, PADK, MB)
+            auto steps = cuda::nd_decompose(c, a.props());
+            if (steps.size() != 1 || !steps[0].fused) {
+                throw bad_configuration("tuned 2d plans need a configuration that runs as one fused tile kernel");
+            }
+            p->impl = std::make_shared<cuda::fft2d_plan>(steps[0].tile, a, jc, tune);
+        } else if (tune && *tune) {
+            if (c.dim != 1) throw bad_configuration("tuned plans are 1d or fused 2d only");
             p->impl = std::make_shared<cuda::fft1d_plan>(c, a, jc, tune);
         } else {
             p->impl = cuda::select_fft_algorithm(c, a, jc);

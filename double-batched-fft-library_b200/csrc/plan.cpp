@@ -350,12 +350,17 @@ std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &
     return steps;
 }
 
-// All steps in one persistent launch (bbk::chain) when they can share a CTA shape.
-// BBFFT_CUDA_ND_CHAIN=0 keeps one launch per step; BBFFT_CUDA_ND_CHAIN_KBLOCK / _CTAS override the
-// slabs per pipeline block and the resident CTAs per SM.
+// All steps in one persistent launch (bbk::chain) when they can share a CTA shape:
+// BBFFT_CUDA_ND_CHAIN=1 (opt-in); BBFFT_CUDA_ND_CHAIN_KBLOCK / _CTAS override the slabs per pipeline
+// block and the resident CTAs per SM.  Measured on the B200 (profiles/r01f_c3c4_chain.jsonl,
+// r01f_ncu_chain3d.txt) the chain does what it was built for -- 3d fp64 64^3 K=64 moves 541 MB
+// through HBM instead of 1074 MB -- but it is not faster yet: 211 us against 190 us for one
+// launch per step, because at the two resident CTAs per SM that the 64 KiB tile step allows the
+// kernels are latency-bound, not bandwidth-bound (issue slots 26 % busy, barrier stalls on top).
+// It stays a switch until the tile step hides its own load latency.
 bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
     char const *env = std::getenv("BBFFT_CUDA_ND_CHAIN");
-    if ((env && *env == '0') || steps.size() < 2 || K_ == 0) return false;
+    if (!(env && *env == '1') || steps.size() < 2 || K_ == 0) return false;
     if (char const *blk = std::getenv("BBFFT_CUDA_ND_BLOCK_BYTES")) {
         if (std::strtoull(blk, nullptr, 10) > 0) return false; // host-side L2 blocking was asked for explicitly
     }

@@ -126,11 +126,11 @@ def test_c2c_nd_fused_equals_multipass_and_l2_blocking(pkg, monkeypatch, fp, M, 
     xd = torch.from_numpy(x).cuda()
     per_k = x.nbytes // K
     results = {}
-    nochain = {"BBFFT_CUDA_ND_CHAIN": "0"}
-    for name, env in (("default", {}), ("fused", nochain), ("multipass", dict(nochain, BBFFT_CUDA_ND_FUSE="0")),
+    chain = {"BBFFT_CUDA_ND_CHAIN": "1"}
+    for name, env in (("chained", chain), ("fused", {}), ("multipass", {"BBFFT_CUDA_ND_FUSE": "0"}),
                       ("fused-blocked", {"BBFFT_CUDA_ND_BLOCK_BYTES": str(2 * per_k)}),
-                      ("multipass-unblocked", dict(nochain, BBFFT_CUDA_ND_FUSE="0", BBFFT_CUDA_ND_BLOCK_BYTES="0")),
-                      ("multipass-chained", {"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN_KBLOCK": "1"})):
+                      ("multipass-unblocked", {"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_BLOCK_BYTES": "0"}),
+                      ("multipass-chained", dict(chain, BBFFT_CUDA_ND_FUSE="0", BBFFT_CUDA_ND_CHAIN_KBLOCK="1"))):
         for k in ("BBFFT_CUDA_ND_FUSE", "BBFFT_CUDA_ND_BLOCK_BYTES", "BBFFT_CUDA_ND_CHAIN", "BBFFT_CUDA_ND_CHAIN_KBLOCK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -151,12 +151,12 @@ def test_c2c_nd_fused_equals_multipass_and_l2_blocking(pkg, monkeypatch, fp, M, 
         assert rel_l2(y, ref) < TOL[fp], (name, names)
     # one persistent launch for all steps where they can share a CTA shape (bbk::chain); it only
     # changes the schedule, never the arithmetic
-    for name in ("default", "multipass-chained"):
+    for name in ("chained", "multipass-chained"):
         if results[name][1][0].startswith("bbfft_chain"):
             assert results[name][2] == 1 and len(results[name][1]) == 1
     if dim == 3 and M == 1 and Ns[0] >= 32:
-        assert results["default"][1][0].startswith("bbfft_chain2"), results["default"][1]
-    assert np.array_equal(results["default"][0], results["fused"][0])
+        assert results["chained"][1][0].startswith("bbfft_chain2"), results["chained"][1]
+    assert np.array_equal(results["chained"][0], results["fused"][0])
     assert np.array_equal(results["multipass-chained"][0], results["multipass"][0])
     # blocking only changes the launch schedule, never the arithmetic
     assert np.array_equal(results["fused"][0], results["fused-blocked"][0])
@@ -187,7 +187,7 @@ def test_nd_chain_matches_one_launch_per_step(pkg, monkeypatch, fp, ttype, Ns, K
         ref = xr * np.prod(Ns)
         nout, odt, d = ref.size, rdtype(fp), pkg.BACKWARD
     outs = {}
-    for name, env in (("chain", {}), ("steps", {"BBFFT_CUDA_ND_CHAIN": "0"})):
+    for name, env in (("chain", {"BBFFT_CUDA_ND_CHAIN": "1"}), ("steps", {})):
         monkeypatch.delenv("BBFFT_CUDA_ND_CHAIN", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -214,7 +214,7 @@ def test_config4_3d_chain_full_size(pkg, monkeypatch):
     gen.manual_seed(4)
     x = torch.randn(K * 64 * 64 * 64, 2, dtype=torch.float64, device="cuda", generator=gen)
     outs = {}
-    for name, env in (("chain", {}), ("steps", {"BBFFT_CUDA_ND_CHAIN": "0"})):
+    for name, env in (("chain", {"BBFFT_CUDA_ND_CHAIN": "1"}), ("steps", {})):
         monkeypatch.delenv("BBFFT_CUDA_ND_CHAIN", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -220,18 +220,21 @@ def main():
                 bench_real_1d(rows, nm, 4, 16, 256, 1 << 16, stream, ttype, inplace)
     if "c4" in which:
         bench_nd(rows, "C4-3d", 8, (64, 64, 64), 64, stream)
-        bench_nd(rows, "C4-3d-two-launches", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "0"})
-        bench_nd(rows, "C4-3d-multipass", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "0", "BBFFT_CUDA_ND_FUSE": "0"})
-        for kb in (1, 2, 8):
-            bench_nd(rows, "C4-3d-chain-kblock%d" % kb, 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN_KBLOCK": str(kb)})
-        bench_nd(rows, "C4-3d-chain-1cta", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN_CTAS": "1"})
-        bench_nd(rows, "C4-3d-f32-256^3", 4, (256, 256, 256), 8, stream)
-        bench_nd(rows, "C4-3d-f32-256^3-steps", 4, (256, 256, 256), 8, stream, env={"BBFFT_CUDA_ND_CHAIN": "0"})
+        bench_nd(rows, "C4-3d-chained", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "1"})
+        bench_nd(rows, "C4-3d-multipass", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
+        if "chain" in which:
+            for kb in (1, 2, 8):
+                bench_nd(rows, "C4-3d-chain-kblock%d" % kb, 8, (64, 64, 64), 64, stream,
+                         env={"BBFFT_CUDA_ND_CHAIN": "1", "BBFFT_CUDA_ND_CHAIN_KBLOCK": str(kb)})
+            bench_nd(rows, "C4-3d-chain-1cta", 8, (64, 64, 64), 64, stream, env={"BBFFT_CUDA_ND_CHAIN": "1", "BBFFT_CUDA_ND_CHAIN_CTAS": "1"})
+            bench_nd(rows, "C4-3d-f32-256^3-chained", 4, (256, 256, 256), 8, stream, env={"BBFFT_CUDA_ND_CHAIN": "1"})
+            bench_nd(rows, "C4-3d-f32-256^3", 4, (256, 256, 256), 8, stream)
         bench_nd(rows, "C4-2d", 4, (128, 128), 64, stream)
         bench_nd(rows, "C4-2d-big", 4, (128, 128), 8192, stream)
-        bench_nd(rows, "C4-2d-big-chained-passes", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
-        bench_nd(rows, "C4-2d-big-two-launches", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN": "0"})
-        bench_nd(rows, "C4-2d-chained-passes", 4, (128, 128), 64, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
+        bench_nd(rows, "C4-2d-big-multipass", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0"})
+        if "chain" in which:
+            bench_nd(rows, "C4-2d-big-chained-passes", 4, (128, 128), 8192, stream, env={"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN": "1"})
+            bench_nd(rows, "C4-2d-chained-passes", 4, (128, 128), 64, stream, env={"BBFFT_CUDA_ND_FUSE": "0", "BBFFT_CUDA_ND_CHAIN": "1"})
     if "c5" in which:
         for n in (64, 256):
             k = (1 << 30) // (16 * n * 8)

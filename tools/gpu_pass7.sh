@@ -5,6 +5,7 @@ set -u
 TAG=r01f
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/${TAG}_smi.txt 2>&1
+[ -f tune_cache_gpu.tar.xz ] && tar -xJf tune_cache_gpu.tar.xz
 CANDS=$(ls tune_cache_gpu/cands_*.json 2>/dev/null | paste -sd, -)
 NCUBIN=$(ls tune_cache_gpu 2>/dev/null | grep -c cubin)
 echo "pre-compiled candidates on the box: $NCUBIN" | tee $OUT/${TAG}_tune_cache.txt
