@@ -948,6 +948,11 @@ namespace {
 // fewest stages with radices <= rmax (a prime factor above rmax is its own radix), then the
 // cheapest butterflies, then the most balanced split
 std::vector<int> tile_radices(int N, int rmax) {
+    // measured on the B200 (tools/tune_tile.py, profiles/r01g_tile_tune.json): 64 = 4 x 16 beats the
+    // balanced 8 x 8 in the tile kernel by 11 % (fp64, 5215 vs 4701 GB/s) and 13 % (fp32)
+    if (N == 64 && rmax >= 16) return {4, 16};
+    // 32 = 2 x 16 beats 4 x 8: +19 % fp32, +2 % fp64 (profiles/r01h_tile_tune.json)
+    if (N == 32 && rmax >= 16) return {2, 16};
     std::vector<std::vector<int>> facs;
     std::vector<int> cur;
     enum_factorizations(N, std::max(rmax, max_prime(N)), 4, cur, facs);
@@ -1093,7 +1098,9 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     if (tune.count("TH")) {
         p.threads = std::atoi(tune["TH"].c_str());
     } else {
-        const std::uint64_t ept = 16;
+        // fp32 64 x 64 tiles: 128 threads with 32 elements each (four resident CTAs) measured 6273 GB/s
+        // against 5603 GB/s for 256 threads (profiles/r01h_tile_tune.json)
+        const std::uint64_t ept = (p.fp == 4 && tile == 4096) ? 32 : 16;
         int th = 64;
         while (th < dev.max_threads_per_block && std::uint64_t(th) * ept < tile) th *= 2;
         p.threads = th;

@@ -14,6 +14,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -160,6 +162,164 @@ template <typename T> void r2c_c2r(cudaStream_t stream, std::size_t M, std::size
     CHECK(ok);
 }
 
+// test/r2c.cpp:182-252, 299-372 (2d / 3d cases): product of cosines (batch b shifts the frequency of
+// the first mode) -> product of two-delta spectra, r2c forward then c2r backward = prod(N) * input,
+// in-place (padded rows) and out-of-place
+template <typename T, std::size_t D>
+void real_nd(cudaStream_t stream, std::size_t M, std::array<std::size_t, D> N, std::size_t K, bool inplace) {
+    const double tau = 6.28318530717958647692;
+    const std::size_t Nh = N[0] / 2 + 1, N0r = inplace ? 2 * Nh : N[0];
+    std::size_t rest = 1, total = 1;
+    for (std::size_t d = 1; d < D; ++d) rest *= N[d];
+    for (std::size_t d = 0; d < D; ++d) total *= N[d];
+    const std::size_t nreal = M * N0r * rest * K, nspec = M * Nh * rest * K;
+    std::vector<T> x(nreal, T(0));
+    auto freq = [&](std::size_t m, std::size_t k) { return (m + k) % N[0]; };
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t r = 0; r < rest; ++r)
+            for (std::size_t n = 0; n < N[0]; ++n)
+                for (std::size_t m = 0; m < M; ++m) {
+                    double v = std::cos(tau * double(freq(m, k)) * double(n) / double(N[0])) / double(N[0]);
+                    std::size_t rr = r;
+                    for (std::size_t d = 1; d < D; ++d) {
+                        v *= std::cos(tau * double(rr % N[d]) / double(N[d])) / double(N[d]);
+                        rr /= N[d];
+                    }
+                    x[m + M * (n + N0r * (r + rest * k))] = T(v);
+                }
+    tensor_extent shape = {};
+    shape[0] = M;
+    for (std::size_t d = 0; d < D; ++d) shape[d + 1] = N[d];
+    shape[D + 1] = K;
+    configuration cf = {unsigned(D), shape, to_precision_v<T>, direction::forward, transform_type::r2c};
+    cf.set_strides_default(inplace);
+    configuration cb = {unsigned(D), shape, to_precision_v<T>, direction::backward, transform_type::c2r};
+    cb.set_strides_default(inplace);
+    device_vec<T> dreal(std::max(nreal, 2 * nspec));
+    device_vec<std::complex<T>> dspec(nspec);
+    {
+        std::vector<T> up(dreal.n, T(0));
+        std::copy(x.begin(), x.end(), up.begin());
+        dreal.upload(up);
+    }
+    void *spec_ptr = inplace ? static_cast<void *>(dreal.p) : static_cast<void *>(dspec.p);
+    make_plan(cf, stream).execute(dreal.p, spec_ptr).wait();
+    std::vector<std::complex<T>> X(nspec);
+    CUDA_OK(cudaMemcpy(X.data(), spec_ptr, nspec * sizeof(std::complex<T>), cudaMemcpyDeviceToHost));
+    std::size_t nmax = 0;
+    for (std::size_t d = 0; d < D; ++d) nmax = std::max(nmax, N[d]);
+    const double eps = tol<T>(nmax);
+    auto two_delta = [](long k, long f, long n) {
+        return ((k - f) % n == 0 ? 0.5 : 0.0) + ((k + f) % n == 0 ? 0.5 : 0.0);
+    };
+    bool ok = true;
+    for (std::size_t k = 0; k < K && ok; ++k)
+        for (std::size_t r = 0; r < rest && ok; ++r)
+            for (std::size_t n = 0; n < Nh && ok; ++n)
+                for (std::size_t m = 0; m < M && ok; ++m) {
+                    double ref = two_delta(long(n), long(freq(m, k)), long(N[0]));
+                    std::size_t rr = r;
+                    for (std::size_t d = 1; d < D; ++d) {
+                        ref *= two_delta(long(rr % N[d]), 1, long(N[d]));
+                        rr /= N[d];
+                    }
+                    auto v = X[m + M * (n + Nh * (r + rest * k))];
+                    ok = std::abs(double(v.real()) - ref) <= eps && std::abs(double(v.imag())) <= eps;
+                    if (!ok) std::printf("r2c %zud M=%zu K=%zu inplace=%d mismatch at (%zu,%zu,%zu,%zu): %g %g vs %g\n", D, M, K, int(inplace), m, n, r, k, double(v.real()), double(v.imag()), ref);
+                }
+    CHECK(ok);
+    // backward from the exact spectrum we just checked
+    device_vec<T> dback(std::max(nreal, 2 * nspec));
+    void *back_in = inplace ? static_cast<void *>(dreal.p) : static_cast<void *>(dspec.p);
+    void *back_out = inplace ? static_cast<void *>(dreal.p) : static_cast<void *>(dback.p);
+    make_plan(cb, stream).execute(back_in, back_out).wait();
+    std::vector<T> back(nreal);
+    CUDA_OK(cudaMemcpy(back.data(), back_out, nreal * sizeof(T), cudaMemcpyDeviceToHost));
+    ok = true;
+    for (std::size_t k = 0; k < K && ok; ++k)
+        for (std::size_t r = 0; r < rest && ok; ++r)
+            for (std::size_t n = 0; n < N[0] && ok; ++n)
+                for (std::size_t m = 0; m < M && ok; ++m) {
+                    const std::size_t i = m + M * (n + N0r * (r + rest * k));
+                    ok = std::abs(double(back[i]) - double(x[i]) * double(total)) <= eps * 4;
+                }
+    CHECK(ok);
+}
+
+// test/callback.cpp:18-114 (load) and :116-202 (store): a c2r plan whose load callback implies a
+// zero upper half of the spectrum equals the plain plan on the zero-padded spectrum, and an r2c
+// plan whose store callback keeps the first N/4 bins scaled by 1/N equals the truncated, scaled
+// plain result -- both compared with == (the transform arithmetic is the same code)
+template <typename T> void callbacks_bit_identical(cudaStream_t stream, std::size_t M, std::size_t N) {
+    const std::size_t K = 4;
+    char const *real = sizeof(T) == 4 ? "float" : "double";
+    unsigned s = 777;
+    auto rnd = [&] {
+        s = s * 1664525u + 1013904223u;
+        return T((s >> 8) & 0xffff) / T(65536);
+    };
+    {
+        const std::size_t Next = 2 * N, ns_ref = Next / 2 + 1, ns = N / 2 + 1;
+        std::vector<std::complex<T>> X(M * ns * K), Xref(M * ns_ref * K, std::complex<T>(0, 0));
+        for (std::size_t k = 0; k < K; ++k)
+            for (std::size_t n = 0; n < ns; ++n)
+                for (std::size_t m = 0; m < M; ++m) {
+                    X[m + M * (n + ns * k)] = {rnd(), rnd()};
+                    Xref[m + M * (n + ns_ref * k)] = X[m + M * (n + ns * k)];
+                }
+        std::ostringstream src;
+        src << real << "2 load(global " << real << "2* in, size_t offset) {\n"
+            << "    size_t m = offset % " << M << ";\n    size_t n = offset / " << M << " % " << ns_ref << ";\n"
+            << "    size_t k = offset / " << (M * ns_ref) << ";\n"
+            << "    if (n < " << ns << ") { return in[m + " << M << " * (n + " << ns << " * k)]; }\n"
+            << "    return 0;\n}\n";
+        const std::string code = src.str();
+        configuration ref = {1, {M, Next, K}, to_precision_v<T>, direction::backward, transform_type::c2r,
+                             {1, M, M * ns_ref}, {1, M, M * Next}};
+        configuration cb = ref;
+        cb.callbacks = {code.c_str(), code.size(), "load", nullptr};
+        device_vec<std::complex<T>> dX(X.size()), dXref(Xref.size());
+        device_vec<T> dx(M * Next * K), dxref(M * Next * K);
+        dX.upload(X);
+        dXref.upload(Xref);
+        make_plan(ref, stream).execute(dXref.p, dxref.p).wait();
+        make_plan(cb, stream).execute(dX.p, dx.p).wait();
+        CHECK(dx.download() == dxref.download());
+    }
+    {
+        const std::size_t N2 = 4 * N, ncut = N2 / 4, nspec = N2 / 2 + 1;
+        std::vector<T> x(M * N2 * K);
+        for (auto &v : x) v = rnd();
+        std::ostringstream src;
+        src << "void store(global " << real << "2* out, size_t offset, " << real << "2 value) {\n"
+            << "    size_t m = offset % " << M << ";\n    size_t n = offset / " << M << " % " << nspec << ";\n"
+            << "    size_t k = offset / " << (M * nspec) << ";\n"
+            << "    if (n < " << ncut << ") { out[m + " << M << " * (n + " << ncut << " * k)] = value * ((" << real << ") "
+            << std::hexfloat << (1.0 / double(N2)) << std::defaultfloat << "); }\n}\n";
+        const std::string code = src.str();
+        configuration ref = {1, {M, N2, K}, to_precision_v<T>, direction::forward, transform_type::r2c,
+                             {1, M, M * N2}, {1, M, M * nspec}};
+        configuration cb = ref;
+        cb.callbacks = {code.c_str(), code.size(), nullptr, "store"};
+        device_vec<T> dx(x.size());
+        device_vec<std::complex<T>> dref(M * nspec * K), dcut(M * ncut * K);
+        dx.upload(x);
+        make_plan(ref, stream).execute(dx.p, dref.p).wait();
+        make_plan(cb, stream).execute(dx.p, dcut.p).wait();
+        auto full = dref.download();
+        auto cut = dcut.download();
+        bool ok = true;
+        const T scale = T(1.0 / double(N2));
+        for (std::size_t k = 0; k < K && ok; ++k)
+            for (std::size_t n = 0; n < ncut && ok; ++n)
+                for (std::size_t m = 0; m < M && ok; ++m) {
+                    auto want = full[m + M * (n + nspec * k)] * scale;
+                    ok = cut[m + M * (n + ncut * k)] == want;
+                }
+        CHECK(ok);
+    }
+}
+
 int main() {
     int ndev = 0;
     CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -195,6 +355,37 @@ int main() {
         for (std::size_t N : {2u, 4u, 5u, 8u, 27u, 16u, 128u, 105u, 256u, 102u, 26u}) {
             r2c_c2r<float>(stream, M, N, 33);
             r2c_c2r<double>(stream, M, N, 33);
+        }
+
+    // --- real 2d / 3d, the reference's case lists (test/r2c.cpp:206-252 forward, :338-372 backward)
+    for (std::size_t M : {1u, 3u})
+        for (std::size_t K : {1u, 33u}) {
+            for (auto N : {std::array<std::size_t, 2>{4, 8}, std::array<std::size_t, 2>{8, 5}}) {
+                real_nd<float, 2>(stream, M, N, K, true);
+                real_nd<double, 2>(stream, M, N, K, true);
+            }
+            for (auto N : {std::array<std::size_t, 3>{4, 8, 2}, std::array<std::size_t, 3>{8, 256, 5}}) {
+                real_nd<float, 3>(stream, M, N, K, true);
+                real_nd<double, 3>(stream, M, N, K, true);
+            }
+        }
+    for (std::size_t M : {1u, 7u})
+        for (std::size_t K : {1u, 65u}) {
+            for (auto N : {std::array<std::size_t, 2>{5, 4}, std::array<std::size_t, 2>{10, 3}}) {
+                real_nd<float, 2>(stream, M, N, K, false);
+                real_nd<double, 2>(stream, M, N, K, false);
+            }
+            for (auto N : {std::array<std::size_t, 3>{5, 4, 6}, std::array<std::size_t, 3>{10, 286, 3}}) {
+                real_nd<float, 3>(stream, M, N, K, false);
+                real_nd<double, 3>(stream, M, N, K, false);
+            }
+        }
+
+    // --- callbacks, bit-identical to the plain plans (test/callback.cpp sizes: M in {1,32}, N in {8,64,212})
+    for (std::size_t M : {1u, 32u})
+        for (std::size_t N : {8u, 64u, 212u}) {
+            callbacks_bit_identical<float>(stream, M, N);
+            callbacks_bit_identical<double>(stream, M, N);
         }
 
     // --- errors (test/error.cpp:13-21, small_batch_fft.hpp:107-110)

@@ -30,12 +30,24 @@ def main():
             if m:
                 dflt = None if m.group(5) == "n/a" else float(m.group(5))
                 entries[(int(m.group(1)), int(m.group(2)))] = (m.group(3), float(m.group(4)), dflt)
+    if args.keep_existing and os.path.exists(args.real_out):
+        import re as _re
+        for line in open(args.real_out):
+            m = _re.match(r'\{(\d+), (\d+), (\d+), 0, "([^"]*)"\}, // (\d+) GB/s \(heuristic (\S+)\)', line)
+            if m:
+                dflt = None if m.group(6) == "n/a" else float(m.group(6))
+                real_entries[(int(m.group(1)), int(m.group(2)), int(m.group(3)))] = (m.group(4), float(m.group(5)), dflt)
     for f in args.files:
         for key, v in json.load(open(f)).items():
             parts = key.split(",")
             if len(parts) == 3:
                 # "r2c,fp,N" / "c2r,fp,N": measured real-transform entries go to wisdom_real.inc
                 tkey = ({"r2c": 1, "c2r": 2}[parts[0]], int(parts[1]), int(parts[2]))
+                if args.keep_existing and tkey in real_entries and v.get("mode") == "interleaved":
+                    cur = real_entries[tkey][0]
+                    cur_gbs = dict((t, g) for t, g in v.get("top", [])).get(cur)
+                    if v["best"] == cur or (cur_gbs and v["gbs"] < cur_gbs * (1.0 + args.min_switch)):
+                        continue
                 real_entries.pop(tkey, None)
                 if v["best"] and not (v.get("default_gbs") and v["gbs"] < v["default_gbs"] * (1.0 + args.min_gain)):
                     real_entries[tkey] = (v["best"], v["gbs"], v.get("default_gbs"))

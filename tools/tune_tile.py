@@ -14,14 +14,14 @@ pkg = importlib.import_module("double-batched-fft-library_b200")
 
 CASES = {
     # descriptor: candidate overrides ("" = planner default)
-    "dcfo64x64*4096": ["", "TH=512,MB=2", "TH=512,MB=1", "TH=1024,MB=1", "TH=256,MB=1", "RA=4x16,RB=4x16", "RA=4x16,RB=4x16,TH=512,MB=2",
-                       "RA=16x4,RB=16x4,TH=512,MB=2", "RA=4x4x4,RB=4x4x4,TH=512,MB=2", "RA=4x4x4,RB=4x4x4,TH=1024,MB=1",
-                       "TH=512,MB=2,PADK=16", "TH=512,MB=2,PADK=0"],
-    "scfo128x128*8192": ["", "TH=512,MB=1", "RA=16x8,RB=16x8", "RA=4x4x8,RB=4x4x8", "RA=8x16,RB=8x16,PADK=32", "RA=8x16,RB=8x16,PADK=8",
-                         "RA=2x8x8,RB=2x8x8"],
-    "scfo64x64*32768": ["", "TH=512,MB=2", "TH=512,MB=3", "TH=256,MB=4", "TH=128,MB=4", "TH=1024,MB=2", "RA=4x16,RB=4x16"],
-    "dcfo32x32*65536": ["", "TH=128,MB=4", "TH=256,MB=4", "TH=64,MB=8", "TH=128,MB=8"],
-    "scfo16.32x48*5461": ["", "TH=512,MB=1", "TH=1024,MB=1"],
+    "dcfo64x64*4096": ["", "RA=8x8,RB=8x8", "TH=128,MB=2", "TH=512,MB=2", "RA=2x32,RB=2x32", "RA=4x16,RB=8x8", "RA=8x8,RB=4x16",
+                       "RA=4x16,RB=4x16,PADK=8", "RA=4x16,RB=4x16,PADK=32", "RA=4x16,RB=4x16,PADK=64", "RA=4x16,RB=4x16,MB=1"],
+    "scfo128x128*8192": ["", "RA=4x32,RB=4x32", "RA=8x16,RB=4x32", "RA=4x32,RB=8x16", "RA=4x32,RB=4x32,TH=512,MB=1"],
+    "scfo64x64*32768": ["", "RA=8x8,RB=8x8", "TH=128,MB=4", "TH=128,MB=6", "TH=256,MB=4", "TH=64,MB=6", "RA=2x32,RB=2x32",
+                        "RA=2x32,RB=2x32,TH=128,MB=4"],
+    "dcfo32x32*65536": ["", "RA=2x16,RB=2x16", "RA=2x16,RB=2x16,TH=64,MB=8"],
+    "scfo32x32*131072": ["", "RA=2x16,RB=2x16", "RA=32,RB=32", "TH=128,MB=8"],
+    "scfo256x64*8192": ["", "RA=8x32,RB=4x16", "RA=16x16,RB=8x8"],
 }
 
 
