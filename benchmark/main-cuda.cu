@@ -341,24 +341,37 @@ template <typename T, bool Real> static void run_case(options const &o, unsigned
             CUFFT_OK(cufftPlanMany(&s.cplan, 1, &n, &inembed, int(M), idist, &onembed, int(M), odist, type, int(s.K)));
             CUFFT_OK(cufftSetStream(s.cplan, s.stream));
         }
+        // cuFFT rejects a real tensor whose m-th column starts off an 8 (16) byte boundary
+        // (CUFFT_INVALID_VALUE for odd m): strided real transforms with M > 1 are then reported
+        // as unsupported instead of aborting the sweep
+        bool cufft_supported = true;
         auto exec = [&]() {
             for (auto &s : slabs) {
                 if (s.K == 0) continue;
                 CUDA_OK(cudaSetDevice(s.device));
-                for (unsigned i = 0; i < M; ++i) {
+                for (unsigned i = 0; i < M && cufft_supported; ++i) {
                     char *xi = static_cast<char *>(s.x) + i * sig_elem;
                     char *Xi = static_cast<char *>(s.X) + i * spec_elem;
-                    if (o.inverse) CUFFT_OK(cufftXtExec(s.cplan, Xi, xi, CUFFT_INVERSE));
-                    else CUFFT_OK(cufftXtExec(s.cplan, xi, Xi, CUFFT_FORWARD));
+                    cufftResult r = o.inverse ? cufftXtExec(s.cplan, Xi, xi, CUFFT_INVERSE)
+                                              : cufftXtExec(s.cplan, xi, Xi, CUFFT_FORWARD);
+                    if (r == CUFFT_INVALID_VALUE && Real && M > 1) {
+                        cufft_supported = false;
+                    } else if (r != CUFFT_SUCCESS) {
+                        CUFFT_OK(r);
+                    }
                 }
             }
             sync_all();
         };
         initialise();
         exec();
-        const bool ok = check();
-        const double ns = bench(exec);
-        emit("cufft", ns, ok);
+        if (cufft_supported) {
+            const bool ok = check();
+            const double ns = bench(exec);
+            emit("cufft", ns, ok);
+        } else {
+            std::fprintf(stderr, "cufft: strided real transform with M = %u not supported (misaligned columns), skipped\n", M);
+        }
         for (auto &s : slabs) {
             if (s.cplan) cufftDestroy(s.cplan);
             s.cplan = 0;

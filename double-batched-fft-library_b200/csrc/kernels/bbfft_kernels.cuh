@@ -397,6 +397,19 @@ template <class C> struct batch_index {
     bool ok;
 };
 
+#ifdef BBFFT_EMU
+#define BBK_SYNC() ::bbfft_emu::syncthreads()
+#define BBK_TID() (::bbfft_emu::thread_idx())
+#define BBK_BID() (::bbfft_emu::block_idx())
+#define BBK_SMEM() (::bbfft_emu::shared_mem())
+#else
+#define BBK_SYNC() __syncthreads()
+#define BBK_TID() (int(threadIdx.x))
+#define BBK_BID() (u64(blockIdx.x))
+#define BBK_SMEM() (bbk_dyn_smem)
+extern __shared__ __align__(16) unsigned char bbk_dyn_smem[];
+#endif
+
 // One Stockham pass.  SRC/DST select where the elements come from / go to.
 enum : int {
     IO_GLOBAL = 0,  // complex tensor in global memory
@@ -458,7 +471,7 @@ BBK_DEV void store_elem(args const &a, u64 m, u64 k, int bin, cx<typename C::rea
 }
 
 template <class C, int S, int SRC, int DST>
-BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
+BBK_DEV void run_stage_regs(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
                        bool ok) {
     using T = typename C::real_t;
     using G = geom<C>;
@@ -542,18 +555,86 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
     }
 }
 
-#ifdef BBFFT_EMU
-#define BBK_SYNC() ::bbfft_emu::syncthreads()
-#define BBK_TID() (::bbfft_emu::thread_idx())
-#define BBK_BID() (::bbfft_emu::block_idx())
-#define BBK_SMEM() (::bbfft_emu::shared_mem())
-#else
-#define BBK_SYNC() __syncthreads()
-#define BBK_TID() (int(threadIdx.x))
-#define BBK_BID() (u64(blockIdx.x))
-#define BBK_SMEM() (bbk_dyn_smem)
-extern __shared__ __align__(16) unsigned char bbk_dyn_smem[];
-#endif
+
+// A stage whose radix is a prime too large for an in-register butterfly (> 31: the O(p^2) unrolled
+// butterfly would not fit the register file; the reference unrolls such primes into one work-item
+// and lets the compiler spill).  The sub-FFTs are direct DFTs done cooperatively: the stage's
+// inputs sit in shared memory, every thread accumulates ceil(N/T) OUTPUTS (sum_j x[j] w_R^(jq),
+// w from a table of R entries), one barrier, then the outputs take the inputs' places (or go to
+// global memory).  O(R) multiply-adds per element: slow next to the smooth sizes, but every N works.
+template <class C, int S, int SRC, int DST>
+BBK_DEV void run_stage_direct(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    constexpr int R = C::radix(S);
+    constexpr int NS = G::ns(S);
+    constexpr int NS1 = NS / R;
+    constexpr int NSUB = C::N / R;
+    constexpr bool LAST = (S == C::L - 1);
+    constexpr int OUTS = (C::N + C::T - 1) / C::T;
+    const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + C::tw_off(S);
+    const cx<T> *BBK_RESTRICT twd = reinterpret_cast<const cx<T> *>(a.tw) + C::tw_dir(S);
+    if constexpr (SRC != IO_SMEM) {
+        static_for<0, OUTS>([&](auto ii) {
+            const int pos = t + C::T * decltype(ii)::value;
+            if (C::N % C::T == 0 || pos < C::N) sm[G::soff(b, pos)] = load_elem<C, SRC>(a, m, k, pos, ok);
+        });
+        BBK_SYNC();
+    }
+    cx<T> acc[OUTS];
+    static_for<0, OUTS>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int o = t + C::T * i;
+        acc[i] = cx<T>{T(0), T(0)};
+        if (C::N % C::T == 0 || o < C::N) {
+            // consecutive threads take consecutive sub-FFTs (consecutive shared-memory positions)
+            const int u = o % NSUB, q = o / NSUB;
+            const int base = (u / NS1) * NS + u % NS1;
+            cx<T> s = sm[G::soff(b, base)];
+            int idx = 0;
+            for (int j = 1; j < R; ++j) {
+                idx += q;
+                if (idx >= R) idx -= R;
+                const cx<T> x = sm[G::soff(b, base + NS1 * j)];
+                const cx<T> w = ldg_cx(twd + idx);
+                s.x = ffma(x.x, w.x, s.x);
+                s.x = ffma(-x.y, w.y, s.x);
+                s.y = ffma(x.x, w.y, s.y);
+                s.y = ffma(x.y, w.x, s.y);
+            }
+            acc[i] = s;
+        }
+    });
+    BBK_SYNC(); // every input is read before an output takes its place
+    static_for<0, OUTS>([&](auto ii) {
+        constexpr int i = decltype(ii)::value;
+        const int o = t + C::T * i;
+        if (C::N % C::T == 0 || o < C::N) {
+            const int u = o % NSUB, q = o / NSUB;
+            const int n2 = u % NS1;
+            cx<T> v = acc[i];
+            if constexpr (!LAST) {
+                if (q > 0) v = cmul(v, ldg_cx(tw + (q - 1) * NS1 + n2));
+            }
+            if constexpr (DST == IO_SMEM) {
+                sm[G::soff(b, (u / NS1) * NS + n2 + NS1 * q)] = v;
+            } else {
+                static_assert(LAST, "only the last stage stores to global memory");
+                store_elem<C, DST>(a, m, k, bin_of_sub<C>(u) + (C::N / R) * q, v, ok);
+            }
+        }
+    });
+}
+
+template <class C, int S, int SRC, int DST>
+BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
+                       bool ok) {
+    if constexpr (C::direct(S)) {
+        run_stage_direct<C, S, SRC, DST>(a, sm, t, b, m, k, ok);
+    } else {
+        run_stage_regs<C, S, SRC, DST>(a, sm, t, b, m, k, ok);
+    }
+}
 
 // stages S..L-1 with all intermediate exchanges in shared memory
 template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {

@@ -46,6 +46,8 @@ bool radix_supported(int r) {
     return true;
 }
 
+bool direct_radix(int r) { return r > 31 && max_prime(r) == r; }
+
 static int pow2_ceil(std::uint64_t x) {
     int p = 1;
     while (std::uint64_t(p) < x && p < (1 << 30)) p <<= 1;
@@ -131,6 +133,7 @@ void enum_factorizations(int n, int max_r, int max_l, std::vector<int> &cur,
     int lo = cur.empty() ? 2 : cur.back(); // ascending
     for (int r = lo; r <= n && r <= max_r; ++r) {
         if (n % r) continue;
+        if (max_prime(r) > 31 && max_prime(r) != r) continue; // a large prime is a stage of its own
         cur.push_back(r);
         enum_factorizations(n / r, max_r, max_l, cur, out);
         cur.pop_back();
@@ -143,6 +146,7 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mir
     const int single_max = (fp == 4) ? 32 : 16; // one thread holds the whole transform
     stage_choice best;
     best.cost = 1e30;
+    const bool has_direct = direct_radix(max_prime(N));
     if (N <= single_max) {
         best.radix = {N};
         best.T = 1;
@@ -158,14 +162,16 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mir
     // complex elements per thread before adding a stage.
     const int ebase = fp == 4 ? 32 : 20;
     for (int relax = 0; relax < 4 && best.radix.empty(); ++relax) {
-        const int emax = std::max(ebase << relax, max_prime(N)); // complex elements per thread
+        // complex elements per thread (a large prime is not held in registers: direct stage)
+        const int emax = std::max(ebase << relax, has_direct ? 0 : max_prime(N));
+        const int rmax_enum = std::max(emax, max_prime(N));
         const int tmax = max_threads_per_transform << relax;
         std::vector<std::vector<int>> facs;
         std::vector<int> cur;
-        enum_factorizations(N, emax, 4, cur, facs);
+        enum_factorizations(N, rmax_enum, 4, cur, facs);
         for (auto const &f : facs) {
             int L = int(f.size());
-            if (L < 2 && N > 64) continue;
+            if (L < 2 && N > 64 && !direct_radix(N)) continue;
             if (mirror_max > 0 && L > 1 && f.front() > mirror_max) continue; // f is ascending
             std::set<int> tcand;
             for (int r : f) {
@@ -175,6 +181,10 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mir
                 }
             }
             if (L == 1) tcand = {1};
+            if (has_direct) {
+                // a direct stage deals OUTPUTS to the threads: any thread count works
+                for (int c = 4; c <= 16; c *= 2) tcand.insert((N + c - 1) / c);
+            }
             for (int T : tcand) {
                 if (T < 1 || T > tmax) continue;
                 int regs = 0, rsum = 0;
@@ -182,9 +192,14 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mir
                 for (int r : f) {
                     int nsub = N / r;
                     int cnt = (nsub + T - 1) / T;
-                    regs = std::max(regs, cnt * r);
+                    if (direct_radix(r)) {
+                        regs = std::max(regs, (N + T - 1) / T);
+                        work += 0.5 * r; // O(r) multiply-adds per element
+                    } else {
+                        regs = std::max(regs, cnt * r);
+                        work += double(cnt) * T * r / N * radix_cost(r);
+                    }
                     rsum += r;
-                    work += double(cnt) * T * r / N * radix_cost(r);
                 }
                 if (regs > emax) continue;
                 // cost: arithmetic (counting idle lanes) + exchange passes + mild preferences
@@ -325,6 +340,7 @@ struct layout_eval {
 void choose_smem_layout(kernel_params &p) {
     const int elem_bytes = 2 * p.fp;
     bool uses_smem = p.L > 1 || p.load_staged || p.store_staged || p.mode != k_c2c;
+    for (int s = 0; s < p.L; ++s) uses_smem = uses_smem || direct_radix(p.radix[s]);
     p.LL = (p.klanes || p.ML == 1) ? 1 : p.ML;
     int rowlen = p.N + ((p.mode == k_r2c_half || p.mode == k_c2r_half) ? 1 : 0);
     if (!uses_smem) {
@@ -555,7 +571,10 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     if (p.L > 4) throw std::runtime_error("bbfft-cuda planner: more than 4 stages");
     for (int s = 0; s < 4; ++s) p.radix[s] = s < p.L ? sc.radix[s] : 1;
     p.T = sc.T;
-    if (p.L == 1) p.T = 1;
+    bool has_direct = false;
+    for (int s = 0; s < p.L; ++s) has_direct = has_direct || direct_radix(p.radix[s]);
+    if (p.L == 1 && !has_direct) p.T = 1;
+    if (has_direct && p.T < 2) p.T = std::min(64, p.N); // outputs are dealt to the threads of a transform
 
     // ---- M == 1, single thread per transform: let the lanes walk k
     p.klanes = false;
@@ -630,6 +649,11 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     // (profiles/r01e_real_sweep.jsonl vs r01d), so those keep the separate pass.
     p.real_fused = p.mode != k_c2c && !p.load_staged && !p.store_staged && p.ML > 1;
     if (tune.count("RF")) p.real_fused = p.mode != k_c2c && !p.load_staged && !p.store_staged && std::atoi(tune["RF"].c_str()) != 0;
+    if (p.mode != k_c2c) {
+        // the fused pass runs its stage as in-register butterflies: not for a direct (large prime) stage
+        const bool r2c_mode = p.mode == k_r2c_half || p.mode == k_r2c_double;
+        if (direct_radix(p.radix[r2c_mode ? p.L - 1 : 0])) p.real_fused = false;
+    }
 
     choose_smem_layout(p);
     if (tune.count("PADK") || tune.count("ROW")) {
@@ -654,6 +678,10 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         for (int s = 0; s < p.L; ++s) {
             int nsub = p.N / p.radix[s];
             int cnt = (nsub + p.T - 1) / p.T;
+            if (direct_radix(p.radix[s])) {
+                regs_complex = std::max(regs_complex, (p.N + p.T - 1) / p.T + 2);
+                continue;
+            }
             regs_complex = std::max(regs_complex, (s == 0 ? cnt : 1) * p.radix[s]);
         }
         if (p.real_fused) {
@@ -789,6 +817,20 @@ static std::vector<int> tw_offsets(kernel_params const &p, int *total) {
     return off;
 }
 
+// first complex element of each direct stage's root table (0 for register stages)
+static std::vector<int> tw_dir_offsets(kernel_params const &p) {
+    int total = 0;
+    tw_offsets(p, &total);
+    int acc = total + ((p.mode == k_r2c_half || p.mode == k_c2r_half) ? p.N + 1 : 0);
+    std::vector<int> off(4, 0);
+    for (int s = 0; s < p.L; ++s) {
+        if (!direct_radix(p.radix[s])) continue;
+        off[s] = acc;
+        acc += p.radix[s];
+    }
+    return off;
+}
+
 std::vector<double> make_twiddles(kernel_params const &p) {
     std::vector<double> tw;
     int NS = p.N;
@@ -812,6 +854,16 @@ std::vector<double> make_twiddles(kernel_params const &p) {
         for (int i = 0; i <= p.N; ++i) {
             double re, im;
             unit_root(i, 2L * p.N, p.dir, re, im);
+            tw.push_back(re);
+            tw.push_back(im);
+        }
+    }
+    // direct stages: w_R^(dir k), k = 0..R-1 (after the stage and real tables; offsets: tw_dir_offsets)
+    for (int s = 0; s < p.L; ++s) {
+        if (!direct_radix(p.radix[s])) continue;
+        for (int k = 0; k < p.radix[s]; ++k) {
+            double re, im;
+            unit_root(k, p.radix[s], p.dir, re, im);
             tw.push_back(re);
             tw.push_back(im);
         }
@@ -858,7 +910,14 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     }
     std::set<int> rs;
     for (int s = 0; s < p.L; ++s) rs.insert(p.radix[s]);
-    for (int r : rs) emit_w_table(os, r);
+    for (int r : rs) {
+        if (direct_radix(r)) {
+            os << "struct W" << r << " {\n    static constexpr int n = " << r << ";\n};\n"; // roots come from the table
+        } else {
+            emit_w_table(os, r);
+        }
+    }
+    auto doff = tw_dir_offsets(p);
     int tw_total = 0;
     auto off = tw_offsets(p, &tw_total);
     os << "struct C {\n";
@@ -879,6 +938,11 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
        << p.radix[1] << ", " << p.radix[2] << ", " << p.radix[3] << "};\n        return r[s];\n    }\n";
     os << "    static BBK_CE int tw_off(int s) {\n        constexpr int r[4] = {" << off[0] << ", "
        << off[1] << ", " << off[2] << ", " << off[3] << "};\n        return r[s];\n    }\n";
+    os << "    static BBK_CE bool direct(int s) {\n        constexpr bool r[4] = {" << (direct_radix(p.radix[0]) ? "true" : "false")
+       << ", " << (direct_radix(p.radix[1]) ? "true" : "false") << ", " << (direct_radix(p.radix[2]) ? "true" : "false") << ", "
+       << (direct_radix(p.radix[3]) ? "true" : "false") << "};\n        return r[s];\n    }\n";
+    os << "    static BBK_CE int tw_dir(int s) {\n        constexpr int r[4] = {" << doff[0] << ", " << doff[1] << ", " << doff[2]
+       << ", " << doff[3] << "};\n        return r[s];\n    }\n";
     // per-stage table type
     os << "    template <int S, int Dummy = 0> struct WRsel;\n";
     for (int s = 0; s < p.L; ++s) {

@@ -143,6 +143,10 @@ struct chain_plan_t {
 // Returns false when the steps cannot share one CTA shape (the caller then launches them one by one).
 bool plan_chain(std::vector<chain_step_problem> const &steps, device_props const &dev, chain_plan_t &out);
 
+// A radix that runs as a cooperative direct DFT from shared memory (bbk::run_stage_direct): a prime
+// too large for an in-register butterfly.
+bool direct_radix(int r);
+
 // integer helpers (pinned by tests; semantics of reference src/base/prime_factorization.cpp)
 std::vector<int> prime_factors(int n);
 bool radix_supported(int r);

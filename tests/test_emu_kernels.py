@@ -239,3 +239,26 @@ def test_chain_planning_falls_back(pkg):
             pkg.describe_chain(pkg.parse_descriptor(desc))
     d = pkg.describe_chain(pkg.parse_descriptor("dcfo64x64x64*64"))
     assert d["step_tile"] == [1, 0] and d["per_k"] == [64, 128] and d["threads"] == 256
+
+
+# ---- large prime factors: cooperative direct-DFT stages (bbk::run_stage_direct) ---------------------
+@pytest.mark.parametrize("M,N,K,fp", [(16, 37, 3, 4), (16, 127, 2, 4), (3, 101, 4, 8), (1, 67, 5, 8), (16, 254, 2, 4),
+                                      (2, 424, 2, 4), (1, 509, 2, 4), (4, 509, 1, 8)])
+def test_c2c_large_prime_factor_emulated(pkg, oracle, M, N, K, fp):
+    """Every N works, as in the reference (which unrolls a prime length into one work-item): a prime
+    factor beyond the in-register butterflies becomes a direct-DFT stage out of shared memory."""
+    d = pkg.describe(pkg.make_config(1, [M, N, K], fp, -1, 0, inplace=False))
+    assert max(d["radix"]) > 31 and d["smem_bytes"] > 0
+    for direction in (-1, 1):
+        assert _run_c2c(pkg, oracle, M, N, K, fp, direction) < TOL[fp] * 0.2
+
+
+@pytest.mark.parametrize("ttype", [1, 2])
+@pytest.mark.parametrize("M,N,K,fp", [(16, 74, 3, 4), (16, 202, 2, 4), (1, 254, 4, 4), (3, 127, 4, 8), (1, 127, 5, 4), (2, 106, 3, 8)])
+def test_real_large_prime_factor_emulated(pkg, oracle, ttype, M, N, K, fp):
+    for inplace in (False, True):
+        d = pkg.describe(pkg.make_config(1, [M, N, K], fp, -1 if ttype == 1 else 1, ttype, inplace=inplace))
+        assert "_rf0" in d["identifier"]  # a direct stage is never the fused (mirrored, in-register) one
+        if inplace and d["inplace_unsupported"]:
+            continue
+        assert _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=(ttype == 2)) < TOL[fp] * 0.2

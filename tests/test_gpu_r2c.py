@@ -152,3 +152,12 @@ def test_config3_full_size_round_trip(pkg, inplace):
     assert float((back / N - x[:, :N]).norm() / x[:, :N].norm()) < TOL[4]
     fwd.close()
     bwd.close()
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("ttype", [R2C, C2R])
+@pytest.mark.parametrize("M,N,K", [(16, 74, 33), (16, 202, 20), (1, 254, 100), (3, 127, 40), (1, 127, 51), (16, 509, 10)])
+def test_real_large_prime_factors_vs_oracle(pkg, oracle, fp, ttype, M, N, K):
+    """r2c / c2r with a prime factor beyond the in-register butterflies (direct-DFT stage; the
+    pre/post pass then runs as a separate pass), even and odd N, in- and out-of-place."""
+    test_real_vs_oracle(pkg, oracle, fp, ttype, M, N, K)
