@@ -150,7 +150,7 @@ def run_reference_sample(steps, warmup, threads):
     return fl / dt * 1e-9, by / dt * 1e-9, dt, kind, sample
 
 
-def reference_arm(args):
+def reference_arm(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,7 +170,7 @@ def reference_arm(args):
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(gpus):
@@ -210,8 +210,9 @@ def measure_e2e(args, torch, dist, plans, world, dev, barrier, total_flops):
         t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
-    return {"value": total_flops / t_e2e * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3, "steps": args.e2e_steps,
+    # whole-job figures, like `value`: every rank copies its own slab in and out
+    return {"value": total_flops / t_e2e * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d * world,
+            "d2h_bytes_per_step": d2h * world, "ms_per_step": t_e2e * 1e3, "steps": args.e2e_steps,
             "gbs": (h2d + d2h) * world / t_e2e * 1e-9,
             "api": "bbfft_cuda_plan_execute_host: pinned host buffers, H2D + kernel + D2H per plan, pipelined over k slabs"}
 
@@ -265,8 +266,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (C1, C3, C4, C5)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL prints its version
+    # with NCCL_DEBUG >= VERSION) are sent to stderr for the whole run
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(line + "\n")
+        real_stdout.flush()
+
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, emit)
         return
 
     import torch
@@ -412,7 +423,7 @@ def main():
             "gpu_launches": launches_per_step * steps, "clocks": clocks,
             "other_configs": other,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     for _, _, _, p in plans:
         p.close()
     if world > 1:
