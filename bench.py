@@ -366,9 +366,12 @@ def main():
     for i, (fp, n, k, plan) in enumerate(plans):
         ts = sorted(per[s][i][0].elapsed_time(per[s][i][1]) * 1e-3 for s in range(steps))
         avg = sum(ts) / len(ts)
-        kernel_time += avg
+        med = ts[len(ts) // 2]
+        kernel_time += avg  # roofline.achieved: algorithmic bytes / AVERAGE launch duration
         b = 2.0 * M_BATCH * n * k * 2 * fp
-        rows.append((fp, n, k, avg, b / avg * 1e-9, flops_c2c(n, M_BATCH * k) / avg * 1e-9, plan.kernel_names[0]))
+        # the per-size table reports the median: one hiccup in one of the timed steps (seen once: 2.6 ms on
+        # a 0.33 ms launch, profiles/r01l_per_size.csv fp64 N=63) should not brand a size as slow
+        rows.append((fp, n, k, med, b / med * 1e-9, flops_c2c(n, M_BATCH * k) / med * 1e-9, plan.kernel_names[0], avg))
     peak, peak_src = peak_hbm()
     fracs = sorted(r[4] / peak for r in rows)
     worst = min(rows, key=lambda r: r[4])
@@ -380,15 +383,15 @@ def main():
         "kernel": "bbk::fft1d<C> (all 210 instantiations of the sweep, per-launch CUDA events)",
         "algorithmic_bytes_per_launch": "2*N*sizeof(complex)*M*K = 2 GiB",
         "per_size_frac": {"min": fracs[0], "median": fracs[len(fracs) // 2], "max": fracs[-1],
-                          "n_below_0.8": sum(1 for f in fracs if f < 0.8)},
+                          "n_below_0.8": sum(1 for f in fracs if f < 0.8), "statistic": "median over the timed steps"},
         "worst": {"fp": worst[0], "N": worst[1], "GBs": worst[4], "kernel": worst[6]},
     }
     if args.per_size and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.per_size)), exist_ok=True)
         with open(args.per_size, "w") as f:
-            f.write("fp,N,K,time_us,GBs,frac_of_peak,GFLOPs,kernel\n")
+            f.write("fp,N,K,time_us,GBs,frac_of_peak,GFLOPs,kernel,mean_time_us\n")
             for r in rows:
-                f.write("%d,%d,%d,%.2f,%.1f,%.4f,%.1f,%s\n" % (r[0], r[1], r[2], r[3] * 1e6, r[4], r[4] / peak, r[5], r[6]))
+                f.write("%d,%d,%d,%.2f,%.1f,%.4f,%.1f,%s,%.2f\n" % (r[0], r[1], r[2], r[3] * 1e6, r[4], r[4] / peak, r[5], r[6], r[7] * 1e6))
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     e2e = None

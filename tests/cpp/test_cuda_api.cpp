@@ -284,7 +284,20 @@ template <typename T> void callbacks_bit_identical(cudaStream_t stream, std::siz
         dXref.upload(Xref);
         make_plan(ref, stream).execute(dXref.p, dxref.p).wait();
         make_plan(cb, stream).execute(dX.p, dx.p).wait();
-        CHECK(dx.download() == dxref.download());
+        auto got = dx.download(), want = dxref.download();
+        std::size_t ndiff = 0, first = 0;
+        for (std::size_t i = 0; i < got.size(); ++i) {
+            if (!(got[i] == want[i])) {
+                if (!ndiff) first = i;
+                ++ndiff;
+            }
+        }
+        if (ndiff) {
+            std::printf("load callback %s M=%zu N=%zu: %zu of %zu elements differ, first at (m=%zu, n=%zu, k=%zu): %.9g vs %.9g\n",
+                        real, M, N, ndiff, got.size(), first % M, first / M % Next, first / (M * Next), double(got[first]),
+                        double(want[first]));
+        }
+        CHECK(ndiff == 0);
     }
     {
         const std::size_t N2 = 4 * N, ncut = N2 / 4, nspec = N2 / 2 + 1;

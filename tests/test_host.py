@@ -140,3 +140,42 @@ def test_builtin_bundle_meets_planned_occupancy(pkg):
             assert warps_per_partition // ((warps + 3) // 4) >= mb, (name, reg)
             assert stack <= 128, (name, stack)
     assert seen >= 216
+
+
+def test_persistent_kernel_cache(pkg, tmp_path, monkeypatch):
+    """BBFFT_CUDA_KERNEL_CACHE: an NVRTC result is stored under a hash of (header, stub, arch, options)
+    and served from disk afterwards; a different stub or option set gets a different file."""
+    import os
+    d = pkg.describe(pkg.parse_descriptor("scfo16.12*7"))
+    plain = pkg.compile_to_cubin(d["source"])
+    monkeypatch.setenv("BBFFT_CUDA_KERNEL_CACHE", str(tmp_path))
+    first = pkg.compile_to_cubin(d["source"])
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].endswith(".cubin") and first == plain
+    # a hit returns the stored bytes: make them recognisable
+    path = os.path.join(tmp_path, files[0])
+    with open(path, "rb") as f:
+        stored = f.read()
+    assert stored == first
+    with open(path, "wb") as f:
+        f.write(stored + b"\0")
+    assert pkg.compile_to_cubin(d["source"]) == stored + b"\0"
+    # other stub, other options: other entries
+    pkg.compile_to_cubin(pkg.describe(pkg.parse_descriptor("scfo16.12*7"), "R=3x4,T=3")["source"])
+    monkeypatch.setenv("BBFFT_CUDA_JIT_LINEINFO", "0")
+    small = pkg.compile_to_cubin(d["source"])
+    assert len(os.listdir(tmp_path)) == 3 and len(small) < len(first)
+
+
+def test_every_length_plans(pkg):
+    """Like the reference, no N is refused: primes beyond the in-register butterflies become
+    direct-DFT stages (radix > 31 in the identifier) and always sit in a stage of their own."""
+    for n in (37, 53, 67, 101, 127, 254, 379, 424, 509, 2 * 251):
+        for fp in (4, 8):
+            d = pkg.describe(pkg.make_config(1, [16, n, 8], fp, pkg.FORWARD, pkg.C2C, inplace=False))
+            prod = 1
+            for r in d["radix"]:
+                prod *= r
+                big = [p for p in range(32, r + 1) if r % p == 0 and all(p % q for q in range(2, int(p ** 0.5) + 1))]
+                assert not big or big == [r], (n, d["radix"])
+            assert prod == n and d["smem_bytes"] > 0
