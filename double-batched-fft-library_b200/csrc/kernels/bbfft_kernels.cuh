@@ -45,6 +45,15 @@
 #define BBK_RESTRICT __restrict__
 #endif
 
+// Shared-memory pointer type.  In product builds it is a plain pointer; the CPU emulator's race
+// checker (tests/emu, -DBBFFT_EMU_RACECHECK) substitutes a proxy that records which thread read or
+// wrote every word between two barriers.
+#if defined(BBFFT_EMU) && defined(BBFFT_EMU_RACECHECK)
+#define BBK_SPTR(E) ::bbfft_emu::checked_ptr<E>
+#else
+#define BBK_SPTR(E) E *
+#endif
+
 namespace bbk {
 
 typedef unsigned long long u64;
@@ -130,6 +139,14 @@ BBK_DEV cx<double> ldcg_cx(const cx<double> *p) {
     return cx<double>{r.x, r.y};
 }
 #endif
+
+template <class E> BBK_DEV BBK_SPTR(E) sptr(void *p) {
+#if defined(BBFFT_EMU) && defined(BBFFT_EMU_RACECHECK)
+    return ::bbfft_emu::checked_ptr<E>{static_cast<E *>(p)};
+#else
+    return static_cast<E *>(p);
+#endif
+}
 
 template <int I> struct ic {
     static constexpr int value = I;
@@ -471,7 +488,7 @@ BBK_DEV void store_elem(args const &a, u64 m, u64 k, int bin, cx<typename C::rea
 }
 
 template <class C, int S, int SRC, int DST>
-BBK_DEV void run_stage_regs(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
+BBK_DEV void run_stage_regs(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k,
                        bool ok) {
     using T = typename C::real_t;
     using G = geom<C>;
@@ -563,7 +580,7 @@ BBK_DEV void run_stage_regs(args const &a, cx<typename C::real_t> *sm, int t, in
 // w from a table of R entries), one barrier, then the outputs take the inputs' places (or go to
 // global memory).  O(R) multiply-adds per element: slow next to the smooth sizes, but every N works.
 template <class C, int S, int SRC, int DST>
-BBK_DEV void run_stage_direct(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+BBK_DEV void run_stage_direct(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     using T = typename C::real_t;
     using G = geom<C>;
     constexpr int R = C::radix(S);
@@ -627,7 +644,7 @@ BBK_DEV void run_stage_direct(args const &a, cx<typename C::real_t> *sm, int t, 
 }
 
 template <class C, int S, int SRC, int DST>
-BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k,
+BBK_DEV void run_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k,
                        bool ok) {
     if constexpr (C::direct(S)) {
         run_stage_direct<C, S, SRC, DST>(a, sm, t, b, m, k, ok);
@@ -637,7 +654,7 @@ BBK_DEV void run_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, 
 }
 
 // stages S..L-1 with all intermediate exchanges in shared memory
-template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     if constexpr (S < C::L) {
         constexpr int SRC = (S == 0) ? SRC0 : IO_SMEM;
         constexpr int DST = (S == C::L - 1) ? DSTL : IO_SMEM;
@@ -651,7 +668,7 @@ template <class C, int S, int SRC0, int DSTL> BBK_DEV void run_stages(args const
 
 // stages S..END-1, all of them writing to shared memory (the caller runs stage END itself)
 template <class C, int S, int END, int SRC0>
-BBK_DEV void run_front_stages(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+BBK_DEV void run_front_stages(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     if constexpr (S < END) {
         constexpr int SRC = (S == 0) ? SRC0 : IO_SMEM;
         if constexpr (S > 0) {
@@ -686,7 +703,7 @@ template <class C> BBK_DEV int sub_of_bin(int k0) {
 // Units p = 0 .. NB/2 (resp. NS1/2); p = 0 and 2p = NB are their own mirrors.
 // ------------------------------------------------------------------------------------------
 template <class C, int SRC>
-BBK_DEV void r2c_last_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+BBK_DEV void r2c_last_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     using T = typename C::real_t;
     using G = geom<C>;
     constexpr int S = C::L - 1;
@@ -785,7 +802,7 @@ BBK_DEV void r2c_last_stage(args const &a, cx<typename C::real_t> *sm, int t, in
 }
 
 template <class C, int DST>
-BBK_DEV void c2r_first_stage(args const &a, cx<typename C::real_t> *sm, int t, int b, u64 m, u64 k, bool ok) {
+BBK_DEV void c2r_first_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     using T = typename C::real_t;
     using G = geom<C>;
     constexpr int R = C::radix(0);
@@ -944,7 +961,7 @@ BBK_DEV void c2r_first_stage(args const &a, cx<typename C::real_t> *sm, int t, i
 // Cooperative, coalesced copy of the CTA's batch of rows between global and shared memory.
 // NROW = row length in elements of type E, rows are addressed (m, n, k) -> m + n*s1 + k*s2.
 template <class C, class E, int NROW, bool TO_SMEM, bool REVERSE, class LD, class ST>
-BBK_DEV void coop_copy(E *sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, int tid, LD ld, ST st) {
+BBK_DEV void coop_copy(BBK_SPTR(E) sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, int tid, LD ld, ST st) {
     using G = geom<C>;
     // iterate (ml, n, bh) with ml fastest so that consecutive threads touch consecutive addresses
     constexpr int MLC = C::KLANES ? 1 : C::ML;          // m entries per CTA
@@ -976,7 +993,7 @@ BBK_DEV void coop_copy(E *sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, i64 s2, i
 template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
     using T = typename C::real_t;
     using G = geom<C>;
-    cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
     const int tid = BBK_TID();
     const int l0 = tid % C::ML;
     const int t = (tid / C::ML) % C::T;
@@ -1049,7 +1066,8 @@ template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
                 const int p1 = G::soff(b, pos_of_bin<C>(i));
                 const int p2 = G::soff(b, pos_of_bin<C>((H - i) % H));
                 const cx<T> y1 = sm[p1];
-                const cx<T> y2 = conj(sm[p2]);
+                const cx<T> y2r = sm[p2];
+                const cx<T> y2 = conj(y2r);
                 const cx<T> w = ldg_cx(twr + i);
                 const cx<T> iw = cx<T>{-w.y, w.x};
                 const cx<T> aa = rmul(y2 + y1, T(0.5));
@@ -1166,7 +1184,8 @@ template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
             const int i = t + C::T * decltype(cc)::value;
             if (i < PAIRS && okp) {
                 const cx<T> y1 = sm[G::soff(b, pos_of_bin<C>(i))];
-                const cx<T> y2 = conj(sm[G::soff(b, pos_of_bin<C>((C::N - i) % C::N))]);
+                const cx<T> y2r = sm[G::soff(b, pos_of_bin<C>((C::N - i) % C::N))];
+                const cx<T> y2 = conj(y2r);
                 const cx<T> av = rmul(y2 + y1, T(0.5));
                 const cx<T> d = rmul(y2 - y1, T(0.5));
                 const cx<T> bv = cx<T>{-d.y, d.x}; // i * d
@@ -1254,7 +1273,7 @@ template <class P> BBK_CE int pass_ns(int s) {
 }
 
 template <class C, class P, int S, int SRC, int DST>
-BBK_DEV void tile_stage(args const &a, cx<typename C::real_t> *sm, u64 gbase, int tid) {
+BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid) {
     using T = typename C::real_t;
     constexpr int R = P::radix(S);
     constexpr int NS = pass_ns<P>(S);
@@ -1326,7 +1345,7 @@ BBK_DEV void tile_stage(args const &a, cx<typename C::real_t> *sm, u64 gbase, in
 }
 
 template <class C, class P, int S, int SRC0, int DSTL>
-BBK_DEV void tile_pass(args const &a, cx<typename C::real_t> *sm, u64 gbase, int tid) {
+BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid) {
     if constexpr (S < P::L) {
         constexpr int SRC = (S == 0) ? SRC0 : T_SMEM;
         constexpr int DST = (S == P::L - 1) ? DSTL : T_SMEM;
@@ -1340,7 +1359,7 @@ BBK_DEV void tile_pass(args const &a, cx<typename C::real_t> *sm, u64 gbase, int
 
 template <class C> BBK_DEV void fft2d_tile_cta(args const &a, const u64 tile) {
     using T = typename C::real_t;
-    cx<T> *sm = reinterpret_cast<cx<T> *>(BBK_SMEM());
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
     const int tid = BBK_TID();
     const u64 gbase = tile * u64(C::TILE_STRIDE);
     tile_pass<C, typename C::PA, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, gbase, tid);

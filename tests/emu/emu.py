@@ -28,11 +28,15 @@ class Args(C.Structure):
                 ("os2", C.c_longlong)]
 
 
+RACECHECK = os.environ.get("BBFFT_EMU_RACECHECK", "0") == "1"
+
+
 def _compile(desc):
     os.makedirs(_CACHE, exist_ok=True)
     hdr = open(os.path.join(_KERNELS, "bbfft_kernels.cuh")).read()
     runner = open(os.path.join(_HERE, "emu_runner.cpp")).read()
-    key = hashlib.sha1((desc["source"] + hdr + runner).encode()).hexdigest()[:20]
+    shim = open(os.path.join(_HERE, "cuda_emu.hpp")).read()
+    key = hashlib.sha1((desc["source"] + hdr + runner + shim + str(RACECHECK)).encode()).hexdigest()[:20]
     so = os.path.join(_CACHE, key + ".so")
     if not os.path.exists(so):
         stub = os.path.join(_CACHE, key + ".cpp")
@@ -40,6 +44,8 @@ def _compile(desc):
             f.write(desc["source"])
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         extra = ["-DBBFFT_EMU_CHAIN"] if desc["source"].startswith("#define BBFFT_EMU_CHAIN") else []
+        if RACECHECK:
+            extra.append("-DBBFFT_EMU_RACECHECK")
         cmd = [cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DBBFFT_EMU"] + extra + [
                "-DBBFFT_EMU_KERNEL=" + desc["identifier"], "-I" + _HERE, "-I" + _KERNELS, "-include",
                os.path.join(_HERE, "cuda_emu.hpp"), stub, os.path.join(_HERE, "emu_runner.cpp"), "-o",
@@ -63,7 +69,7 @@ def run(cfg, inp, out=None, tune=""):
              cfg.istride[2], cfg.ostride[1], cfg.ostride[2])
     rc = lib.emu_launch(C.byref(a), desc["grid"], desc["threads"], desc["smem_bytes"])
     if rc != 0:
-        raise RuntimeError("emulated kernel failed (rc=%d): divergent barriers" % rc)
+        raise RuntimeError("emulated kernel failed (rc=%d): %s" % (rc, {2: "divergent barriers", 4: "shared-memory race (see stderr)"}.get(rc, "device-side failure")))
     return out, desc
 
 

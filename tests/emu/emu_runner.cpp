@@ -4,9 +4,11 @@
 #include "cuda_emu.hpp"
 #include "bbfft_kernels.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ucontext.h>
+#include <algorithm>
 #include <vector>
 
 // chain kernels (-DBBFFT_EMU_CHAIN) take bbk::chain_args, everything else bbk::args
@@ -21,6 +23,20 @@ namespace bbfft_emu {
 thread_local thread_ctx *current = nullptr;
 unsigned long long grid_size = 1;
 int failed = 0;
+#ifdef BBFFT_EMU_RACECHECK
+word_state *shadow = nullptr;
+unsigned char *shadow_base = nullptr;
+long races = 0;
+int report_unwritten = 0;
+thread_local int epoch = 0;
+void report_race(const char *kind, long word, int other_tid) {
+    if (races < 8) {
+        std::fprintf(stderr, "shared-memory race (%s): word %ld, threads %d and %d, barrier interval %d, CTA %llu\n", kind, word,
+                     other_tid, current->tid, epoch, current->bid);
+    }
+    ++races;
+}
+#endif
 }
 
 namespace {
@@ -30,6 +46,7 @@ struct fiber {
     bbfft_emu::thread_ctx ctx;
     bool done = false;
     char *stack = nullptr;
+    int epoch = 0; // barriers passed (race checker)
 };
 thread_local ucontext_t sched_uc;
 thread_local fiber *running = nullptr;
@@ -37,6 +54,7 @@ thread_local emu_args_t *launch_args = nullptr;
 
 void yield_to_sched(bbfft_emu::thread_ctx *) {
     fiber *f = running;
+    ++f->epoch;
     swapcontext(&f->uc, &sched_uc);
 }
 void fiber_main() {
@@ -57,11 +75,31 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
         f.stack = static_cast<char *>(std::malloc(stack_bytes));
     }
     std::vector<unsigned char> smem(smem_bytes + 64);
+#ifdef BBFFT_EMU_RACECHECK
+    std::vector<bbfft_emu::word_state> shadow_words(smem.size() / 4 + 1);
+    bbfft_emu::shadow = shadow_words.data();
+    bbfft_emu::shadow_base = smem.data();
+    bbfft_emu::races = 0;
+    {
+        char const *u = std::getenv("BBFFT_EMU_UNWRITTEN");
+        bbfft_emu::report_unwritten = (u && *u == '1') ? 1 : 0;
+    }
+#endif
+    // BBFFT_EMU_SMEM_FILL=<byte>: what "uninitialised" shared memory holds; BBFFT_EMU_ORDER=reverse: run
+    // the threads of a barrier interval last-to-first.  A correct kernel's output depends on neither.
+    int fill = 0xcd;
+    if (char const *f = std::getenv("BBFFT_EMU_SMEM_FILL")) fill = std::atoi(f) & 0xff;
+    char const *ord = std::getenv("BBFFT_EMU_ORDER");
+    const bool reverse = ord && ord[0] == 'r';
     for (unsigned long long bid = 0; bid < grid; ++bid) {
-        std::memset(smem.data(), 0xcd, smem.size());
+        std::memset(smem.data(), fill, smem.size());
+#ifdef BBFFT_EMU_RACECHECK
+        std::fill(shadow_words.begin(), shadow_words.end(), bbfft_emu::word_state{});
+#endif
         for (int t = 0; t < threads; ++t) {
             fiber &f = fibers[t];
             f.done = false;
+            f.epoch = 0;
             f.ctx = {t, bid, smem.data(), yield_to_sched};
             getcontext(&f.uc);
             f.uc.uc_stack.ss_sp = f.stack;
@@ -71,11 +109,15 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
         }
         for (;;) {
             int done = 0;
-            for (int t = 0; t < threads; ++t) {
+            for (int tt = 0; tt < threads; ++tt) {
+                const int t = reverse ? threads - 1 - tt : tt;
                 fiber &f = fibers[t];
                 if (!f.done) {
                     running = &f;
                     bbfft_emu::current = &f.ctx;
+#ifdef BBFFT_EMU_RACECHECK
+                    bbfft_emu::epoch = f.epoch;
+#endif
                     swapcontext(&sched_uc, &f.uc);
                 }
                 if (f.done) ++done;
@@ -89,5 +131,8 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
         }
     }
     for (auto &f : fibers) std::free(f.stack);
+#ifdef BBFFT_EMU_RACECHECK
+    if (bbfft_emu::races) return 4;
+#endif
     return bbfft_emu::failed ? 3 : 0;
 }

@@ -262,3 +262,33 @@ def test_real_large_prime_factor_emulated(pkg, oracle, ttype, M, N, K, fp):
         if inplace and d["inplace_unsupported"]:
             continue
         assert _run_real(pkg, oracle, ttype, M, N, K, fp, inplace, pollute=(ttype == 2)) < TOL[fp] * 0.2
+
+
+# ---- robustness of the kernels against what the hardware does not promise ----------------------------
+@pytest.mark.parametrize("desc,tune", [
+    ("scfo16.64*5", ""), ("scfo1.64*40", ""), ("dcfo3.105*7", ""), ("scfo16.254*3", ""), ("scfo1.101*9", ""),
+    ("srfo16.256*3", ""), ("srbo16.256*3", ""), ("srfo1.256*5", ""), ("srbo1.256*5", ""), ("srbi1.16*4", ""), ("srbo1.16*4", ""),
+    ("srbo32.424*4", ""), ("srbo1.424*4", ""), ("srfo3.27*5", ""), ("drbo16.127*4", ""), ("srfo16.64*3", "RF=0"),
+    ("dcfo32x32*3", ""), ("scfo16.32x48*2", ""),
+])
+def test_output_independent_of_smem_garbage_and_thread_order(pkg, monkeypatch, desc, tune):
+    """Shared memory is not zeroed between CTAs and warps run in any order: the result must not
+    change when the emulator pre-fills shared memory with another byte or runs the threads of every
+    barrier interval last-to-first (complements BBFFT_EMU_RACECHECK=1)."""
+    cfg = pkg.parse_descriptor(desc)
+    n = 1
+    for d in range(cfg.dim + 2):
+        n *= cfg.shape[d]
+    rng = np.random.default_rng(11)
+    x = rng.uniform(0, 1, 2 * n + 64).astype(np.float32 if cfg.fp == 4 else np.float64)
+    outs = []
+    for env in ({}, {"BBFFT_EMU_SMEM_FILL": "0"}, {"BBFFT_EMU_SMEM_FILL": "255", "BBFFT_EMU_ORDER": "reverse"}):
+        for k in ("BBFFT_EMU_SMEM_FILL", "BBFFT_EMU_ORDER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        y = np.zeros(2 * n + 64, dtype=x.dtype)
+        emu.run(cfg, x.copy(), y, tune)
+        outs.append(y)
+    assert np.array_equal(outs[0], outs[1], equal_nan=True)
+    assert np.array_equal(outs[0], outs[2], equal_nan=True)
