@@ -91,7 +91,8 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
     if (char const *f = std::getenv("BBFFT_EMU_SMEM_FILL")) fill = std::atoi(f) & 0xff;
     char const *ord = std::getenv("BBFFT_EMU_ORDER");
     const bool reverse = ord && ord[0] == 'r';
-    for (unsigned long long bid = 0; bid < grid; ++bid) {
+    for (unsigned long long bb = 0; bb < grid; ++bb) {
+        const unsigned long long bid = reverse ? grid - 1 - bb : bb; // CTAs run in any order, too
         std::memset(smem.data(), fill, smem.size());
 #ifdef BBFFT_EMU_RACECHECK
         std::fill(shadow_words.begin(), shadow_words.end(), bbfft_emu::word_state{});

@@ -269,12 +269,13 @@ def test_real_large_prime_factor_emulated(pkg, oracle, ttype, M, N, K, fp):
     ("scfo16.64*5", ""), ("scfo1.64*40", ""), ("dcfo3.105*7", ""), ("scfo16.254*3", ""), ("scfo1.101*9", ""),
     ("srfo16.256*3", ""), ("srbo16.256*3", ""), ("srfo1.256*5", ""), ("srbo1.256*5", ""), ("srbi1.16*4", ""), ("srbo1.16*4", ""),
     ("srbo32.424*4", ""), ("srbo1.424*4", ""), ("srfo3.27*5", ""), ("drbo16.127*4", ""), ("srfo16.64*3", "RF=0"),
-    ("dcfo32x32*3", ""), ("scfo16.32x48*2", ""),
+    ("dcfo32x32*3", ""), ("scfo16.32x48*2", ""), ("srfi16.30*5", ""), ("srbi16.30*5", ""), ("drfi3.27*5", ""), ("srfi32.100*3", ""),
+    ("srbi1.256*6", ""), ("drbo5.11*4", ""), ("scfo17.12*3", ""),
 ])
 def test_output_independent_of_smem_garbage_and_thread_order(pkg, monkeypatch, desc, tune):
     """Shared memory is not zeroed between CTAs and warps run in any order: the result must not
-    change when the emulator pre-fills shared memory with another byte or runs the threads of every
-    barrier interval last-to-first (complements BBFFT_EMU_RACECHECK=1)."""
+    change when the emulator pre-fills shared memory with another byte or runs the CTAs, and the threads
+    of every barrier interval, last-to-first (complements BBFFT_EMU_RACECHECK=1)."""
     cfg = pkg.parse_descriptor(desc)
     n = 1
     for d in range(cfg.dim + 2):
@@ -288,7 +289,11 @@ def test_output_independent_of_smem_garbage_and_thread_order(pkg, monkeypatch, d
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         y = np.zeros(2 * n + 64, dtype=x.dtype)
-        emu.run(cfg, x.copy(), y, tune)
+        if desc[3] == "i":
+            y[:] = x  # in-place configurations transform their own buffer
+            emu.run(cfg, y, None, tune)
+        else:
+            emu.run(cfg, x.copy(), y, tune)
         outs.append(y)
     assert np.array_equal(outs[0], outs[1], equal_nan=True)
     assert np.array_equal(outs[0], outs[2], equal_nan=True)
