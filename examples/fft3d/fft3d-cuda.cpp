@@ -11,7 +11,7 @@
 //     K         batch of independent 3d transforms (default 1)
 //
 // Build: g++ -std=c++17 -I include -I $CUDA_HOME/include fft3d-cuda.cpp -L <libdir> -lbbfft_cuda
-//        -L $CUDA_HOME/lib64 -lcufft -lcudart  (tests/test_gpu_cpp_api.py does exactly this)
+//        -L $CUDA_HOME/lib64 -lcufft -lcudart  (tests/test_gpu_examples.py does exactly this)
 #include "bbfft/configuration.hpp"
 #include "bbfft/cuda/make_plan.hpp"
 

@@ -2,7 +2,7 @@
 // make_plan, plan::execute, jit_cache_all, aot_cache, generate_fft_kernels, callbacks) on CUDA.
 // Re-hosts the checks of the reference's device tests (test/c2c.cpp:17-127, test/r2c.cpp,
 // test/callback.cpp:18-114, test/error.cpp:13-21, examples/cache/main.cpp, examples/aot/main.cpp)
-// with cudaMalloc instead of sycl::malloc_device.  Built and run by tests/test_gpu_cpp_api.py.
+// with cudaMalloc instead of sycl::malloc_device.  Built and run by tests/test_gpu_z_cpp_api.py (named to run last: a long binary).
 #include "bbfft/aot_cache.hpp"
 #include "bbfft/bad_configuration.hpp"
 #include "bbfft/configuration.hpp"
@@ -296,6 +296,13 @@ template <typename T> void callbacks_bit_identical(cudaStream_t stream, std::siz
             std::printf("load callback %s M=%zu N=%zu: %zu of %zu elements differ, first at (m=%zu, n=%zu, k=%zu): %.9g vs %.9g\n",
                         real, M, N, ndiff, got.size(), first % M, first / M % Next, first / (M * Next), double(got[first]),
                         double(want[first]));
+            // which side moved?  (diagnostic only: the check below still fails)
+            make_plan(ref, stream).execute(dXref.p, dxref.p).wait();
+            make_plan(cb, stream).execute(dX.p, dx.p).wait();
+            auto got2 = dx.download(), want2 = dxref.download();
+            std::printf("  second execution: callback plan %s, plain plan %s, callback == plain: %s\n",
+                        got2 == got ? "reproduced itself" : "CHANGED", want2 == want ? "reproduced itself" : "CHANGED",
+                        got2 == want2 ? "yes" : "no");
         }
         CHECK(ndiff == 0);
     }

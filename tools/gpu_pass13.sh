@@ -10,7 +10,7 @@ timeout 300 python tools/tune_list.py --cases tools/cases_c1.json --inner 20 --f
 unset BBFFT_CUDA_KERNEL_CACHE BBFFT_CUDA_JIT_LINEINFO BBFFT_CUDA_NO_WISDOM
 # the full tier ran green on the previous state (profiles/r01i_pytest.log); this pass re-runs the files that the
 # direct-DFT stages and the planner changes touch (everything except the large analytic/callback matrices)
-timeout 1200 python -m pytest tests/test_gpu_c2c.py tests/test_gpu_nd.py tests/test_gpu_examples.py tests/test_gpu_cpp_api.py -m gpu -x -q \
+timeout 1200 python -m pytest tests/test_gpu_c2c.py tests/test_gpu_nd.py tests/test_gpu_examples.py tests/test_gpu_z_cpp_api.py -m gpu -x -q \
     -k "not analytic_reference_suite" > $OUT/${TAG}_pytest.log 2>&1; tail -3 $OUT/${TAG}_pytest.log
 timeout 900 python -m pytest tests/test_gpu_r2c.py tests/test_gpu_callback.py -m gpu -x -q -k "large_prime or golden or full_size or vs_oracle or config5" \
     > $OUT/${TAG}_pytest2.log 2>&1; tail -3 $OUT/${TAG}_pytest2.log
