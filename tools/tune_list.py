@@ -13,6 +13,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# same planning environment as tools/warm_cache.py, so that pre-compiled candidates are cache hits
+os.environ["BBFFT_CUDA_NO_WISDOM"] = "1"
+os.environ.setdefault("BBFFT_CUDA_JIT_LINEINFO", "0")
+if os.path.isdir(os.path.join(ROOT, "kcache")):
+    os.environ.setdefault("BBFFT_CUDA_KERNEL_CACHE", os.path.join(ROOT, "kcache"))
 pkg = importlib.import_module("double-batched-fft-library_b200")
 
 
@@ -59,8 +64,10 @@ def main():
     y = torch.empty_like(x)
     fillers = []
     if args.filler:
+        os.environ.pop("BBFFT_CUDA_NO_WISDOM", None)  # the sweep's own kernels (built-in bundle)
         for d in ("scfo16.64*131072", "dcfo16.64*65536"):
             fillers.append(pkg.Plan(pkg.parse_descriptor(d), stream=stream))
+        os.environ["BBFFT_CUDA_NO_WISDOM"] = "1"
     times = {}
     nf = 0
     import random

@@ -19,12 +19,18 @@ def main():
     ap.add_argument("items", nargs="*")
     ap.add_argument("--tile-cases", action="store_true")
     ap.add_argument("--real-sweep", action="store_true")
+    ap.add_argument("--with-wisdom", action="store_true", help="plan like the library does by default (bench / sweep kernels)")
     ap.add_argument("--cases", action="append", default=[], help="JSON {descriptor: [overrides]} (tools/tune_list.py)")
     ap.add_argument("--dir", default=os.path.join(ROOT, "kcache"))
     args = ap.parse_args()
     os.makedirs(args.dir, exist_ok=True)
     os.environ["BBFFT_CUDA_KERNEL_CACHE"] = args.dir
     os.environ["BBFFT_CUDA_JIT_LINEINFO"] = "0"
+    # candidates are planned without the measured tables on both sides (tools/tune_list.py sets the same):
+    # a wisdom entry merged into an override string here but not on the GPU box would change the kernel
+    # and with it the cache key (that cost the config-3 search of round 1 its GPU time)
+    if not args.with_wisdom:
+        os.environ["BBFFT_CUDA_NO_WISDOM"] = "1"
     pkg = importlib.import_module("double-batched-fft-library_b200")
     jobs = [tuple(i.split(":", 1)) if ":" in i else (i, "") for i in args.items]
     if args.real_sweep:
