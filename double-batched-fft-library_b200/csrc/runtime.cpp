@@ -115,9 +115,9 @@ static std::vector<std::uint8_t> nvrtc_compile_uncached(std::string const &sourc
                                                         std::vector<std::string> const &extra_options);
 
 std::vector<std::uint8_t> nvrtc_compile(std::string const &source, std::string const &arch,
-                                        std::vector<std::string> const &extra_options) {
+                                        std::vector<std::string> const &extra_options, bool refresh) {
     const std::string path = disk_cache_path(source, arch, extra_options);
-    if (!path.empty()) {
+    if (!path.empty() && !refresh) {
         std::ifstream f(path, std::ios::binary);
         if (f) {
             std::vector<std::uint8_t> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -339,7 +339,15 @@ std::string api::arch() const {
 
 shared_handle<module_handle_t> api::build_module(std::string const &source) const {
     auto bin = nvrtc_compile(source, arch(), {});
-    return make_shared_handle(load_module_image(bin.data()));
+    try {
+        return make_shared_handle(load_module_image(bin.data()));
+    } catch (error const &) {
+        // a damaged entry of the persistent kernel cache must not break plan creation: compile again
+        // (overwriting the entry) and let a second failure propagate
+        if (!std::getenv("BBFFT_CUDA_KERNEL_CACHE")) throw;
+        bin = nvrtc_compile(source, arch(), {}, true);
+        return make_shared_handle(load_module_image(bin.data()));
+    }
 }
 
 cudaKernel_t api::create_kernel(module_handle_t mod, std::string const &name, std::size_t smem_bytes) const {

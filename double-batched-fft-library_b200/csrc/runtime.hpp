@@ -68,8 +68,9 @@ class api {
 };
 
 // NVRTC (dlopen'ed).  Throws bbfft::cuda::error with the build log on failure.
+// `refresh` bypasses (and overwrites) the persistent kernel cache entry.
 std::vector<std::uint8_t> nvrtc_compile(std::string const &source, std::string const &arch,
-                                        std::vector<std::string> const &extra_options);
+                                        std::vector<std::string> const &extra_options, bool refresh = false);
 // The device header text (kernels/bbfft_kernels.cuh), embedded at build time.
 char const *kernel_header_text();
 
