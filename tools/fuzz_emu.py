@@ -1,0 +1,105 @@
+"""Randomised parity check of planned kernels under the CPU emulator against the long-double oracle:
+random (type, precision, direction, M, N, K, strides, in/out-of-place) -- the planner picks the
+kernel -- optionally with random planner overrides.  Test infrastructure, no GPU needed.
+Usage: python tools/fuzz_emu.py --n 200 --seed 1 [--racecheck]"""
+import argparse
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--racecheck", action="store_true")
+    ap.add_argument("--maxn", type=int, default=160)
+    args = ap.parse_args()
+    if args.racecheck:
+        os.environ["BBFFT_EMU_RACECHECK"] = "1"
+    import numpy as np
+    import emu
+    from oracle import oracle
+    from common import TOL, rel_l2
+    pkg = emu.pkg
+    rnd = random.Random(args.seed)
+    bad = 0
+    for it in range(args.n):
+        ttype = rnd.choice([0, 0, 1, 2])
+        fp = rnd.choice([4, 8])
+        M = rnd.choice([1, 1, 2, 3, 4, 5, 7, 8, 12, 16, 17, 24, 32, 33])
+        N = rnd.randint(2, args.maxn)
+        K = rnd.randint(1, 9)
+        d = rnd.choice([-1, 1]) if ttype == 0 else (-1 if ttype == 1 else 1)
+        inplace = rnd.random() < 0.4
+        nspec = N // 2 + 1
+        # default strides, or padded ones (c2c only: the real layouts are pinned by the in-place rule)
+        kw = {}
+        if ttype == 0 and rnd.random() < 0.3:
+            s1 = M + rnd.randint(0, 3)
+            s2 = s1 * N + rnd.randint(0, 5)
+            kw = dict(istride=[1, s1, s2], ostride=[1, s1, s2] if inplace else [1, M, M * N])
+        try:
+            cfg = pkg.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace, **kw) if not kw else \
+                pkg.make_config(1, [M, N, K], fp, d, ttype, **kw)
+            desc = pkg.describe(cfg)
+        except Exception as ex:
+            print("plan rejected:", ttype, fp, M, N, K, inplace, kw, str(ex)[:80])
+            bad += 1
+            continue
+        if inplace and desc["inplace_unsupported"]:
+            continue
+        ocfg = oracle.make_config(1, [M, N, K], fp, d, ttype, inplace=inplace, **kw) if not kw else \
+            oracle.make_config(1, [M, N, K], fp, d, ttype, **kw)
+        rng = np.random.default_rng(it)
+        rdt = np.float32 if fp == 4 else np.float64
+        cdt = np.complex64 if fp == 4 else np.complex128
+        ist, ost = list(cfg.istride)[:3], list(cfg.ostride)[:3]
+        in_elems = ist[2] * K + 8
+        out_elems = ost[2] * K + 8
+        if ttype == 1:
+            x = rng.standard_normal(max(in_elems, 2 * out_elems)).astype(rdt)
+        else:
+            x = (rng.standard_normal(max(in_elems, out_elems)) + 1j * rng.standard_normal(max(in_elems, out_elems))).astype(cdt)
+        if ttype == 2 and N % 2 == 0:
+            # a valid c2r input has a real Nyquist bin (imag(X[0]) may be polluted: it is ignored by
+            # definition, reference test/r2c.cpp:310-324; imag(X[N/2]) is not)
+            for k in range(K):
+                for m in range(M):
+                    idx = m + (N // 2) * ist[1] + k * ist[2]
+                    x[idx] = x[idx].real
+        try:
+            if inplace:
+                buf, ref = x.copy(), x.copy()
+                emu.run(cfg, buf, None)
+                oracle.dft(ocfg, ref)
+                got, want = buf.view(rdt), ref.view(rdt)
+            else:
+                odt = rdt if ttype == 2 else cdt
+                got = np.zeros(out_elems, odt)
+                want = np.zeros(out_elems, odt)
+                emu.run(cfg, x, got)
+                oracle.dft(ocfg, x, want)
+                got, want = got.view(rdt), want.view(rdt)
+            # in-place buffers keep untouched input in their gaps: compare where the oracle wrote or left equal
+            err = rel_l2(got, want)
+        except Exception as ex:
+            print("FAILED to run:", ttype, fp, M, N, K, inplace, kw, desc["identifier"], str(ex)[:120])
+            bad += 1
+            continue
+        ok = err < TOL[fp] * 0.5
+        if not ok:
+            bad += 1
+        print("%s type=%d fp=%d M=%d N=%d K=%d dir=%d inplace=%d %s err=%.2e %s" % (
+            "ok  " if ok else "BAD ", ttype, fp, M, N, K, d, inplace, kw or "", err, desc["identifier"][6:70]), flush=True)
+    print("done: %d problems" % bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
