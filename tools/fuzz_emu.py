@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--racecheck", action="store_true")
     ap.add_argument("--maxn", type=int, default=160)
+    ap.add_argument("--nd", type=int, default=0, help="additional random 2d / 3d c2c configurations (tile kernel, chain)")
     args = ap.parse_args()
     if args.racecheck:
         os.environ["BBFFT_EMU_RACECHECK"] = "1"
@@ -97,6 +98,44 @@ def main():
             bad += 1
         print("%s type=%d fp=%d M=%d N=%d K=%d dir=%d inplace=%d %s err=%.2e %s" % (
             "ok  " if ok else "BAD ", ttype, fp, M, N, K, d, inplace, kw or "", err, desc["identifier"][6:70]), flush=True)
+    # ---- 2d / 3d: fused tile kernel and chained plans (c2c, default layout)
+    for it in range(args.nd):
+        fp = rnd.choice([4, 8])
+        dim = rnd.choice([2, 2, 3])
+        M = rnd.choice([1, 1, 2, 3])
+        Ns = [rnd.choice([4, 6, 8, 9, 10, 12, 15, 16, 20, 24, 27, 32, 36, 48, 64]) for _ in range(dim)]
+        K = rnd.randint(1, 4)
+        d = rnd.choice([-1, 1])
+        cfg = pkg.make_config(dim, [M] + Ns + [K], fp, d, 0, inplace=False)
+        cdt = np.complex64 if fp == 4 else np.complex128
+        rng = np.random.default_rng(1000 + it)
+        shape_np = (K,) + tuple(reversed(Ns)) + (M,)
+        x = (rng.standard_normal(shape_np) + 1j * rng.standard_normal(shape_np)).astype(cdt)
+        axes = tuple(range(1, dim + 1))
+        ref = np.fft.fftn(x.astype(np.complex128), axes=axes) if d < 0 else np.fft.ifftn(x.astype(np.complex128), axes=axes) * np.prod(Ns)
+        y = np.zeros_like(x)
+        what = None
+        try:
+            if dim == 2:
+                try:
+                    _, desc = emu.run(cfg, x.reshape(-1), y.reshape(-1))
+                    what = desc["identifier"]
+                except pkg.BadConfiguration:
+                    pass
+            if what is None:
+                try:
+                    _, desc, _ = emu.run_chain(cfg, x.reshape(-1), y.reshape(-1), kblock=rnd.randint(1, 3), epochs=rnd.randint(1, 2))
+                    what = desc["identifier"]
+                except pkg.BadConfiguration:
+                    continue  # neither a single fused kernel nor chainable: one launch per step, covered by the 1d runs
+        except Exception as ex:
+            print("FAILED to run nd:", fp, M, Ns, K, str(ex)[:160])
+            bad += 1
+            continue
+        err = rel_l2(y, ref)
+        ok = err < TOL[fp] * 0.5
+        bad += 0 if ok else 1
+        print("%s nd fp=%d M=%d N=%s K=%d dir=%d err=%.2e %s" % ("ok  " if ok else "BAD ", fp, M, Ns, K, d, err, what[:70]), flush=True)
     print("done: %d problems" % bad)
     return 1 if bad else 0
 
