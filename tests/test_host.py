@@ -179,3 +179,14 @@ def test_every_length_plans(pkg):
                 big = [p for p in range(32, r + 1) if r % p == 0 and all(p % q for q in range(2, int(p ** 0.5) + 1))]
                 assert not big or big == [r], (n, d["radix"])
             assert prod == n and d["smem_bytes"] > 0
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/bbfft_cuda.h is the FFI boundary: it must compile as C99 without any C++ or CUDA header."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "bbfft_cuda.h"\nint main(void) { bbfft_cuda_config c; (void)c; return bbfft_cuda_last_error() == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
