@@ -36,3 +36,17 @@ def test_cpp_api_on_device(pkg):
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=1500)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_empty_batch_executes_as_a_no_op(pkg):
+    """K = 0: plan creation succeeds, execute launches nothing and leaves the output untouched."""
+    cfg = pkg.make_config(1, [16, 64, 0], 4, pkg.FORWARD, pkg.C2C, inplace=False)
+    import torch
+    plan = pkg.Plan(cfg, stream=torch.cuda.current_stream().cuda_stream)
+    x = torch.zeros(8, dtype=torch.complex64, device="cuda")
+    y = torch.full((8,), 3.0, dtype=torch.complex64, device="cuda")
+    plan.execute(x, y)
+    torch.cuda.synchronize()
+    assert bool((y == 3.0).all())
+    plan.close()

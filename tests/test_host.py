@@ -190,3 +190,14 @@ def test_c_abi_header_is_plain_c(tmp_path):
     src.write_text('#include "bbfft_cuda.h"\nint main(void) { bbfft_cuda_config c; (void)c; return bbfft_cuda_last_error() == 0; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
                            "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_empty_batch_plans_to_an_empty_grid(pkg):
+    """K = 0 is a valid (empty) batch: the plan exists and launches nothing; an empty FFT shape is refused."""
+    for shape, ttype, d in (([16, 64, 0], pkg.C2C, pkg.FORWARD), ([1, 8, 0], pkg.C2C, pkg.BACKWARD), ([16, 30, 0], pkg.R2C, pkg.FORWARD)):
+        desc = pkg.describe(pkg.make_config(1, shape, 4, d, ttype, inplace=False))
+        assert desc["grid"] == 0
+    import pytest
+    for shape in ([0, 64, 4], [16, 0, 4]):
+        with pytest.raises(pkg.BadConfiguration):
+            pkg.describe(pkg.make_config(1, shape, 4, pkg.FORWARD, pkg.C2C, inplace=False))
