@@ -665,6 +665,14 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         p.smem_bytes = std::size_t(groups) * p.ROW * elem_bytes;
     }
     if (p.smem_bytes > dev.max_smem_per_block) {
+        // long transforms with many batch lanes: halve the lanes (shorter rows per access, same
+        // kernel family) until the CTA's rows fit, unless the caller pinned the lane count
+        auto given = parse_tune(tune_str);
+        if (p.ML > 1 && !p.klanes && prob.M > 1 && (!given.count("ML") || given.count("MLAUTO"))) {
+            // (MLAUTO marks a lane count chosen here, not by the caller: it may be narrowed again)
+            std::string narrower = tune_str + (tune_str.empty() ? "" : ",") + "MLAUTO=1,ML=" + std::to_string(p.ML / 2);
+            return plan_kernel_1d(prob, dev, narrower);
+        }
         throw std::runtime_error("bbfft-cuda planner: shared memory demand too large");
     }
     // Resident CTAs: a stage-synchronised CTA cannot overlap its own load and compute phases, so

@@ -297,3 +297,12 @@ def test_output_independent_of_smem_garbage_and_thread_order(pkg, monkeypatch, d
         outs.append(y)
     assert np.array_equal(outs[0], outs[1], equal_nan=True)
     assert np.array_equal(outs[0], outs[2], equal_nan=True)
+
+
+@pytest.mark.parametrize("M,N,K,fp", [(16, 2048, 1, 4), (16, 2048, 1, 8), (1, 4096, 2, 4)])
+def test_c2c_beyond_512_emulated(pkg, oracle, M, N, K, fp):
+    """N > 512 stays one kernel while a transform fits shared memory (the reference's f2fft kernel has
+    the same bound); with many batch lanes the planner narrows the lanes until the CTA's rows fit."""
+    d = pkg.describe(pkg.make_config(1, [M, N, K], fp, -1, 0, inplace=False))
+    assert d["smem_bytes"] <= 227 * 1024 and (M == 1 or d["batch_lanes"] < 128 // (2 * fp) or N * 128 <= 227 * 1024)
+    assert _run_c2c(pkg, oracle, M, N, K, fp, -1) < TOL[fp] * 0.2
