@@ -1,7 +1,7 @@
 // bbfft_kernels.cuh -- hand-written sm_100a device templates for the double-batched small FFT.
 //
 // This single header is the whole device side of the library.  It is
-//   * compiled by NVRTC at plan creation (the host embeds this text; see jit.cpp),
+//   * compiled by NVRTC at plan creation (the host embeds this text; see runtime.cpp),
 //   * compiled by nvcc for the built-in / AOT kernel bundles (same text, same stubs),
 //   * compiled by g++ against tests/emu/cuda_emu.hpp (macro BBFFT_EMU) so that every index
 //     map can be checked on a CPU-only box.  That emulation is test infrastructure only.
@@ -16,7 +16,9 @@
 //   fft1d, L >= 2         <- src/base/generator/f2fft_gen.cpp:46-183   ("factor2 slm" kernel)
 //   real pre/post passes  <- sbfft_gen.cpp:162-351, f2fft_gen.cpp:228-502
 //   C::ld / C::st hooks   <- src/base/generator/tensor_accessor.cpp:34-55 (callback_accessor)
-// The algorithm is NOT a translation: stages are radix-2..16 Stockham-style passes that work in
+//   fft2d_tile, chain     <- src/common/algorithm/nd_fft.hpp:66-152 (2d / 3d as chained 1d launches)
+//   run_stage_direct      <- prime lengths, which the reference unrolls into one work-item
+// The algorithm is NOT a translation: stages are radix-2..32 Stockham-style passes that work in
 // place in shared memory (digit reversal folded into the final store), threads are laid out so
 // that the M batch index runs along the lanes of a warp (coalesced 128-byte rows, conflict-free
 // shared memory without padding), and twiddles between stages come from a small L1-resident
