@@ -243,6 +243,10 @@ def other_configs(peak):
         bc.bench_nd(rows, "C4 2d shape at 1 GiB", 4, (128, 128), 8192, stream)
         bc.bench_c2c_1d(rows, "C5 c2c f32 M=16 N=256 identity load/store callbacks", 4, 16, 256, (1 << 30) // (16 * 256 * 8),
                         stream, callbacks=(bc.IDENTITY_CB % dict(v="float2"), "load", "store", "cuda"))
+        try:  # last, and optional: a failed stream capture must not cost the rows above
+            bc.bench_c2c_1d_graph(rows, "C1 1d c2c f32 N=64 M=1 K=16384 (L2 resident)", 4, 1, 64, 16384, stream)
+        except Exception:
+            pass
     out = []
     for r in rows:
         out.append({"config": r["config"] + (" " + r["note"] if r["note"] else ""), "GBs": round(r["GBs"], 1),

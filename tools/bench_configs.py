@@ -104,6 +104,29 @@ def bench_c2c_1d(rows, name, fp, M, N, K, stream, callbacks=None, inplace=False,
     plan.close()
 
 
+def bench_c2c_1d_graph(rows, name, fp, M, N, K, stream, launches=20):
+    """The same plan with `launches` executes captured in one CUDA graph: what a launch-bound caller
+    (small, L2-resident batches) gets when it replays a graph instead of launching kernel by kernel."""
+    x = torch.view_as_complex(torch.rand(K, N, M, 2, dtype=rdt(fp), device="cuda"))
+    y = torch.empty_like(x)
+    cfg = pkg.make_config(1, [M, N, K], fp, pkg.FORWARD, pkg.C2C, inplace=False)
+    plan = pkg.Plan(cfg, stream=stream)
+    plan.execute(x, y)
+    torch.cuda.synchronize()
+    err = rel_l2(y[: min(K, 32)], torch.fft.fft(x[: min(K, 32)].to(torch.complex128), dim=1))
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(launches):
+            plan.execute(x, y, stream=torch.cuda.current_stream().cuda_stream)
+    tb, tm = time_fn(graph.replay, inner=1)
+    nbytes = 2.0 * M * N * K * 2 * fp
+    flops = 5.0 * N * math.log2(N) * M * K
+    report(rows, name, fp, (M, N, K), nbytes, flops, tb / launches, tm / launches, None, err, plan.kernel_names,
+           "per launch, %d launches replayed as one CUDA graph" % launches)
+    plan.close()
+
+
 def bench_real_1d(rows, name, fp, M, N, K, stream, ttype, inplace, cufft=True):
     nh = N // 2 + 1
     d = pkg.FORWARD if ttype == pkg.R2C else pkg.BACKWARD
@@ -244,6 +267,11 @@ def main():
         for (m, n) in ((16, 16), (1120, 32), (128, 512), (70, 16)):
             k = max(1, int(512e6) // (16 * m * n))
             bench_c2c_1d(rows, "C5-tft-shape", 8, m, n, k, stream, note="tft.cpp shape")
+    if "c1" in which:
+        try:  # last: a failed stream capture must not cost the rows above
+            bench_c2c_1d_graph(rows, "C1-graph", 4, 1, 64, 16384, stream)
+        except Exception as ex:
+            print("C1-graph failed:", str(ex)[:200], file=sys.stderr)
     if args.real_sweep:
         sizes = [n for n in aot.smooth_sizes() if n in (2, 3, 4, 7, 8, 15, 16, 27, 32, 49, 64, 100, 105, 128, 135,
                                                          200, 243, 256, 315, 343, 384, 400, 441, 480, 500, 512)]
