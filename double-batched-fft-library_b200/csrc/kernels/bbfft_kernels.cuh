@@ -43,7 +43,13 @@
 #define BBK_CE __host__ __device__ constexpr
 #define BBK_GLOBAL __global__
 #define BBK_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+// -DBBK_NO_REGCAP: the host rebuilds a JIT kernel without its register cap when the capped build
+// needs local memory (plan.cpp: jit_module)
+#ifdef BBK_NO_REGCAP
+#define BBK_MAXNREG(r)
+#else
 #define BBK_MAXNREG(r) __maxnreg__(r)
+#endif
 #define BBK_RESTRICT __restrict__
 #endif
 
@@ -579,8 +585,8 @@ BBK_DEV void run_stage_regs(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, 
 // butterfly would not fit the register file; the reference unrolls such primes into one work-item
 // and lets the compiler spill).  The sub-FFTs are direct DFTs done cooperatively: the stage's
 // inputs sit in shared memory, every thread accumulates ceil(N/T) OUTPUTS (sum_j x[j] w_R^(jq),
-// w from a table of R entries), one barrier, then the outputs take the inputs' places (or go to
-// global memory).  O(R) multiply-adds per element: slow next to the smooth sizes, but every N works.
+// w from a table of R entries); outputs of the last stage go straight to global memory, outputs
+// of an earlier stage take the inputs' places after one barrier.  O(R) multiply-adds per element: slow next to the smooth sizes, but every N works.
 template <class C, int S, int SRC, int DST>
 BBK_DEV void run_stage_direct(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int t, int b, u64 m, u64 k, bool ok) {
     using T = typename C::real_t;
@@ -600,49 +606,66 @@ BBK_DEV void run_stage_direct(args const &a, BBK_SPTR(cx<typename C::real_t>) sm
         });
         BBK_SYNC();
     }
-    cx<T> acc[OUTS];
-    static_for<0, OUTS>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int o = t + C::T * i;
-        acc[i] = cx<T>{T(0), T(0)};
-        if (C::N % C::T == 0 || o < C::N) {
-            // consecutive threads take consecutive sub-FFTs (consecutive shared-memory positions)
-            const int u = o % NSUB, q = o / NSUB;
-            const int base = (u / NS1) * NS + u % NS1;
-            cx<T> s = sm[G::soff(b, base)];
-            int idx = 0;
-            for (int j = 1; j < R; ++j) {
-                idx += q;
-                if (idx >= R) idx -= R;
-                const cx<T> x = sm[G::soff(b, base + NS1 * j)];
-                const cx<T> w = ldg_cx(twd + idx);
-                s.x = ffma(x.x, w.x, s.x);
-                s.x = ffma(-x.y, w.y, s.x);
-                s.y = ffma(x.x, w.y, s.y);
-                s.y = ffma(x.y, w.x, s.y);
-            }
-            acc[i] = s;
+    // one output: sum_j x[j] w_R^(j q) of sub-FFT u
+    auto output = [&](int u, int q) {
+        // consecutive threads take consecutive sub-FFTs (consecutive shared-memory positions)
+        const int base = (u / NS1) * NS + u % NS1;
+        cx<T> s = sm[G::soff(b, base)];
+        int idx = 0;
+        for (int j = 1; j < R; ++j) {
+            idx += q;
+            if (idx >= R) idx -= R;
+            const cx<T> x = sm[G::soff(b, base + NS1 * j)];
+            const cx<T> w = ldg_cx(twd + idx);
+            s.x = ffma(x.x, w.x, s.x);
+            s.x = ffma(-x.y, w.y, s.x);
+            s.y = ffma(x.x, w.y, s.y);
+            s.y = ffma(x.y, w.x, s.y);
         }
-    });
-    BBK_SYNC(); // every input is read before an output takes its place
-    static_for<0, OUTS>([&](auto ii) {
-        constexpr int i = decltype(ii)::value;
-        const int o = t + C::T * i;
-        if (C::N % C::T == 0 || o < C::N) {
+        return s;
+    };
+    if constexpr (DST != IO_SMEM) {
+        // Results leave for global memory and nothing in shared memory is overwritten: every
+        // output is stored as soon as it is complete.  A plain loop (two independent sums in
+        // flight) instead of OUTS unrolled accumulators held across a barrier: round 1's unrolled
+        // form made NVRTC 12.9's ptxas spill under __maxnreg__ and emit a store address from a
+        // dead register (fp64 c2r M=32 N=424, profiles/r02b_ptxas_miscompile.md).
+        static_assert(LAST, "only the last stage stores to global memory");
+        constexpr int STEP = 2 * C::T;
+#pragma unroll 1
+        for (int o = t; o < C::N; o += STEP) {
+            const int o2 = o + C::T;
             const int u = o % NSUB, q = o / NSUB;
-            const int n2 = u % NS1;
-            cx<T> v = acc[i];
-            if constexpr (!LAST) {
-                if (q > 0) v = cmul(v, ldg_cx(tw + (q - 1) * NS1 + n2));
-            }
-            if constexpr (DST == IO_SMEM) {
+            const bool two = o2 < C::N;
+            const int u2 = two ? o2 % NSUB : u, q2 = two ? o2 / NSUB : q;
+            const cx<T> v = output(u, q);
+            const cx<T> v2 = output(u2, q2);
+            store_elem<C, DST>(a, m, k, bin_of_sub<C>(u) + (C::N / R) * q, v, ok);
+            if (two) store_elem<C, DST>(a, m, k, bin_of_sub<C>(u2) + (C::N / R) * q2, v2, ok);
+        }
+    } else {
+        cx<T> acc[OUTS];
+        static_for<0, OUTS>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const int o = t + C::T * i;
+            acc[i] = cx<T>{T(0), T(0)};
+            if (C::N % C::T == 0 || o < C::N) acc[i] = output(o % NSUB, o / NSUB);
+        });
+        BBK_SYNC(); // every input is read before an output takes its place
+        static_for<0, OUTS>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const int o = t + C::T * i;
+            if (C::N % C::T == 0 || o < C::N) {
+                const int u = o % NSUB, q = o / NSUB;
+                const int n2 = u % NS1;
+                cx<T> v = acc[i];
+                if constexpr (!LAST) {
+                    if (q > 0) v = cmul(v, ldg_cx(tw + (q - 1) * NS1 + n2));
+                }
                 sm[G::soff(b, (u / NS1) * NS + n2 + NS1 * q)] = v;
-            } else {
-                static_assert(LAST, "only the last stage stores to global memory");
-                store_elem<C, DST>(a, m, k, bin_of_sub<C>(u) + (C::N / R) * q, v, ok);
             }
-        }
-    });
+        });
+    }
 }
 
 template <class C, int S, int SRC, int DST>
@@ -759,6 +782,25 @@ BBK_DEV void r2c_last_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, 
         }
     };
 
+    if constexpr (SRC != IO_SMEM) {
+        // Single-stage kernel (NB == 1: one unit, one thread per transform): it reads and writes
+        // global memory only, and in-place rows of different m overlap, so every load of the CTA
+        // precedes its first store.  The barrier sits outside any thread-dependent branch.
+        static_assert(NB == 1 && C::T == 1, "r2c_last_stage from global memory is the single-stage kernel");
+        cx<T> va[R];
+        fetch(va, 0);
+        BBK_SYNC();
+        reg_fft<T, WR, R, C::DIR>::run(va);
+        emit(0, va[0], va[0]);
+        static_for<1, (R + 1) / 2>([&](auto qq) {
+            constexpr int q = decltype(qq)::value;
+            emit(q, va[q], va[R - q]);
+        });
+        if constexpr (R % 2 == 0) {
+            emit(R / 2, va[R / 2], va[R / 2]);
+        }
+        return;
+    }
     static_for<0, CNTU>([&](auto cc) {
         const int p = t + C::T * decltype(cc)::value;
         if (UNITS % C::T == 0 || p < UNITS) {
@@ -766,11 +808,6 @@ BBK_DEV void r2c_last_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, 
             cx<T> va[R], vb[R];
             fetch(va, sub_of_bin<C>(p));
             if (kb != p) fetch(vb, sub_of_bin<C>(kb));
-            if constexpr (SRC != IO_SMEM) {
-                // single-stage kernels read and write global memory only: in-place rows of
-                // different m overlap, so every load of the CTA precedes its first store
-                BBK_SYNC();
-            }
             reg_fft<T, WR, R, C::DIR>::run(va);
             if (kb != p) {
                 reg_fft<T, WR, R, C::DIR>::run(vb);
@@ -797,8 +834,6 @@ BBK_DEV void r2c_last_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, 
                     emit(p + NB * ((R - 1) / 2), va[(R - 1) / 2], va[(R - 1) / 2]);
                 }
             }
-        } else if constexpr (SRC != IO_SMEM) {
-            BBK_SYNC();
         }
     });
 }

@@ -162,6 +162,21 @@ shared_handle<module_handle_t> builtin_module(std::string const &kernel_name, in
     return {};
 }
 
+// JIT policy: no spills under a register cap.  The planner caps registers with __maxnreg__ so that
+// the planned number of CTAs is resident; when NVRTC's ptxas can only meet the cap by spilling, the
+// kernel is rebuilt without the cap (it then runs with fewer resident CTAs, never with local-memory
+// traffic).  Besides being slow, the spill path of ptxas 12.9 miscompiled one such kernel in round 1
+// (fp64 c2r M=32 N=424 r4x53: an output index rematerialised from a dead register, see
+// profiles/r02b_ptxas_miscompile.md), so capped-and-spilling JIT kernels are not trusted.
+static shared_handle<module_handle_t> jit_module(api const &a, std::string const &source, std::string const &name,
+                                                 std::size_t smem_bytes) {
+    auto mod = a.build_module(source);
+    char const *keep = std::getenv("BBFFT_CUDA_KEEP_REGCAP");
+    if (keep && *keep == '1') return mod;
+    if (a.kernel_local_bytes(a.create_kernel(mod.get(), name, smem_bytes)) == 0) return mod;
+    return a.build_module(source, {"-DBBK_NO_REGCAP"});
+}
+
 static std::string env_tune() {
     char const *t = std::getenv("BBFFT_CUDA_TUNE");
     return t ? std::string(t) : std::string();
@@ -184,7 +199,7 @@ fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::s
     if (cache) module_ = cache->get(key);
     if (!module_ && prob.cb_source.empty()) module_ = builtin_module(kp_.identifier, api_.device());
     if (!module_) {
-        module_ = api_.build_module(kp_.source);
+        module_ = jit_module(api_, kp_.source, kp_.identifier, kp_.p.smem_bytes);
         if (cache) cache->store(key, module_);
     }
     kernel_ = api_.create_kernel(module_.get(), kp_.identifier, kp_.p.smem_bytes);
@@ -288,7 +303,7 @@ fft2d_plan::fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::str
     if (cache) module_ = cache->get(key);
     if (!module_) module_ = builtin_module(tp_.identifier, api_.device());
     if (!module_) {
-        module_ = api_.build_module(tp_.source);
+        module_ = jit_module(api_, tp_.source, tp_.identifier, tp_.p.smem_bytes);
         if (cache) cache->store(key, module_);
     }
     kernel_ = api_.create_kernel(module_.get(), tp_.identifier, tp_.p.smem_bytes);
@@ -388,7 +403,7 @@ bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
     if (cache) chain_module_ = cache->get(key);
     if (!chain_module_) chain_module_ = builtin_module(chain_.identifier, api_.device());
     if (!chain_module_) {
-        chain_module_ = api_.build_module(chain_.source);
+        chain_module_ = jit_module(api_, chain_.source, chain_.identifier, chain_.smem_bytes);
         if (cache) cache->store(key, chain_module_);
     }
     chain_kernel_ = api_.create_kernel(chain_module_.get(), chain_.identifier, chain_.smem_bytes);

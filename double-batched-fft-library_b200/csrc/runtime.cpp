@@ -337,15 +337,22 @@ std::string api::arch() const {
     return os.str();
 }
 
-shared_handle<module_handle_t> api::build_module(std::string const &source) const {
-    auto bin = nvrtc_compile(source, arch(), {});
+std::size_t api::kernel_local_bytes(cudaKernel_t k) const {
+    cudaFuncAttributes attr;
+    BBFFT_CUDA_CHECK(cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(k)));
+    return attr.localSizeBytes;
+}
+
+shared_handle<module_handle_t> api::build_module(std::string const &source,
+                                                 std::vector<std::string> const &options) const {
+    auto bin = nvrtc_compile(source, arch(), options);
     try {
         return make_shared_handle(load_module_image(bin.data()));
     } catch (error const &) {
         // a damaged entry of the persistent kernel cache must not break plan creation: compile again
         // (overwriting the entry) and let a second failure propagate
         if (!std::getenv("BBFFT_CUDA_KERNEL_CACHE")) throw;
-        bin = nvrtc_compile(source, arch(), {}, true);
+        bin = nvrtc_compile(source, arch(), options, true);
         return make_shared_handle(load_module_image(bin.data()));
     }
 }
@@ -402,11 +409,16 @@ void api::release_buffer(void *ptr) const {
 
 void *api::create_twiddle_table(std::vector<double> const &tw, int fp) const {
     void *dev = create_device_buffer(tw.size() * std::size_t(fp));
+    // The copy is issued on the plan's own stream and completed before the plan exists: a
+    // cudaMemcpy from pageable memory may return before its DMA has landed and is ordered on the
+    // legacy stream only, which a cudaStreamNonBlocking user stream does not wait for.
     if (fp == 4) {
         std::vector<float> f(tw.begin(), tw.end());
-        BBFFT_CUDA_CHECK(cudaMemcpy(dev, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+        BBFFT_CUDA_CHECK(cudaMemcpyAsync(dev, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
+        BBFFT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     } else {
-        BBFFT_CUDA_CHECK(cudaMemcpy(dev, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice));
+        BBFFT_CUDA_CHECK(cudaMemcpyAsync(dev, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        BBFFT_CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
     return dev;
 }

@@ -46,7 +46,10 @@ class api {
     std::string arch() const;
 
     // source -> cubin -> loaded module
-    shared_handle<module_handle_t> build_module(std::string const &source) const;
+    shared_handle<module_handle_t> build_module(std::string const &source,
+                                                std::vector<std::string> const &options = {}) const;
+    // bytes of local memory per thread (register spills; the kernels have no local arrays)
+    std::size_t kernel_local_bytes(cudaKernel_t k) const;
     cudaKernel_t create_kernel(module_handle_t mod, std::string const &name, std::size_t smem_bytes) const;
     void launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
                        kernel_args const &args, cudaStream_t stream) const;

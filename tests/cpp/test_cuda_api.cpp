@@ -94,6 +94,66 @@ template <typename T> void c2c_analytic(cudaStream_t stream, std::size_t M, std:
             }
 }
 
+// test/c2c.cpp:65-82 "c2c non-packed forward": strides {1, M+1, (M+1)(N+1)}, same analytic check
+template <typename T> void c2c_nonpacked(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K) {
+    const double tau = 6.28318530717958647692;
+    const std::size_t s1 = M + 1, s2 = (M + 1) * (N + 1);
+    std::vector<std::complex<T>> x(s2 * K, std::complex<T>(T(7), T(-7))); // gaps hold a sentinel
+    for (std::size_t k = 0; k < K; ++k)
+        for (std::size_t n = 0; n < N; ++n)
+            for (std::size_t m = 0; m < M; ++m) {
+                double arg = tau * double((m + k) % N) * double(n) / double(N);
+                double sc = (1.0 + double(k) / double(K)) / double(N);
+                x[m + n * s1 + k * s2] = {T(sc * std::cos(arg)), T(sc * std::sin(arg))};
+            }
+    device_vec<std::complex<T>> d(x.size());
+    d.upload(x);
+    std::array<std::size_t, max_tensor_dim> stride = {1, s1, s2};
+    configuration cfg = {1, {M, N, K}, to_precision_v<T>, direction::forward, transform_type::c2c, stride, stride};
+    make_plan(cfg, stream).execute(d.p).wait();
+    auto X = d.download();
+    double eps = tol<T>(N);
+    bool ok = true;
+    for (std::size_t k = 0; k < K && ok; ++k)
+        for (std::size_t n = 0; n <= N && ok; ++n)
+            for (std::size_t m = 0; m <= M && ok; ++m) {
+                auto v = X[m + n * s1 + k * s2];
+                if (m == M || n == N) {
+                    ok = v == std::complex<T>(T(7), T(-7)); // padding untouched
+                } else {
+                    double ref = (n == (m + k) % N) ? 1.0 + double(k) / double(K) : 0.0;
+                    ok = std::abs(v.real() - ref) <= eps && std::abs(v.imag()) <= eps;
+                }
+            }
+    CHECK(ok);
+}
+
+// test/c2c.cpp:84-127 "c2c identity": forward then backward in place = N * identity
+template <typename T> void c2c_identity_inplace(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K) {
+    std::vector<std::complex<T>> x(M * N * K);
+    unsigned s = 4321;
+    auto rnd = [&] {
+        s = s * 1664525u + 1013904223u;
+        return T((s >> 8) & 0xffff) / T(65536);
+    };
+    for (auto &v : x) v = {rnd(), rnd()};
+    device_vec<std::complex<T>> d(x.size());
+    d.upload(x);
+    configuration cfg = {1, {M, N, K}, to_precision_v<T>, direction::forward};
+    auto plan = make_plan(cfg, stream);
+    cfg.dir = direction::backward;
+    auto iplan = make_plan(cfg, stream);
+    plan.execute(d.p).wait();
+    iplan.execute(d.p).wait();
+    auto y = d.download();
+    double eps = tol<T>(N);
+    bool ok = true;
+    for (std::size_t i = 0; i < x.size() && ok; ++i)
+        ok = std::abs(double(y[i].real()) / N - double(x[i].real())) <= eps * 2 &&
+             std::abs(double(y[i].imag()) / N - double(x[i].imag())) <= eps * 2;
+    CHECK(ok);
+}
+
 // test/c2c.cpp:84-127: forward o backward = N * identity, out-of-place, with event dependencies
 template <typename T> void c2c_identity(cudaStream_t stream, std::size_t M, std::size_t N, std::size_t K) {
     std::vector<std::complex<T>> x(M * N * K);
@@ -166,7 +226,8 @@ template <typename T> void r2c_c2r(cudaStream_t stream, std::size_t M, std::size
 // the first mode) -> product of two-delta spectra, r2c forward then c2r backward = prod(N) * input,
 // in-place (padded rows) and out-of-place
 template <typename T, std::size_t D>
-void real_nd(cudaStream_t stream, std::size_t M, std::array<std::size_t, D> N, std::size_t K, bool inplace) {
+void real_nd(cudaStream_t stream, std::size_t M, std::array<std::size_t, D> N, std::size_t K, bool inplace,
+             bool pollute_0 = false) {
     const double tau = 6.28318530717958647692;
     const std::size_t Nh = N[0] / 2 + 1, N0r = inplace ? 2 * Nh : N[0];
     std::size_t rest = 1, total = 1;
@@ -231,6 +292,12 @@ void real_nd(cudaStream_t stream, std::size_t M, std::array<std::size_t, D> N, s
     // backward from the exact spectrum we just checked
     device_vec<T> dback(std::max(nreal, 2 * nspec));
     void *back_in = inplace ? static_cast<void *>(dreal.p) : static_cast<void *>(dspec.p);
+    if (pollute_0) {
+        // imag(X[0]) != 0 is faulty usage that c2r must ignore (test/r2c.cpp:310-324)
+        for (std::size_t k = 0; k < K; ++k)
+            for (std::size_t m = 0; m < M; ++m) X[m + M * Nh * rest * k].imag(T(1.0 + m + k));
+        CUDA_OK(cudaMemcpy(back_in, X.data(), nspec * sizeof(std::complex<T>), cudaMemcpyHostToDevice));
+    }
     void *back_out = inplace ? static_cast<void *>(dreal.p) : static_cast<void *>(dback.p);
     make_plan(cb, stream).execute(back_in, back_out).wait();
     std::vector<T> back(nreal);
@@ -285,6 +352,29 @@ template <typename T> void callbacks_bit_identical(cudaStream_t stream, std::siz
         make_plan(ref, stream).execute(dXref.p, dxref.p).wait();
         make_plan(cb, stream).execute(dX.p, dx.p).wait();
         auto got = dx.download(), want = dxref.download();
+        {
+            // two plans that are wrong the same way compare equal: hold the plain plan against a
+            // direct DFT as well (columns m = 0 and m = M-1 of every k; imag(X[0]) is ignored)
+            const long double tau = 6.283185307179586476925286766559005768L;
+            bool ok = true;
+            double worst = 0;
+            for (std::size_t k = 0; k < K; ++k)
+                for (std::size_t m : {std::size_t(0), M - 1})
+                    for (std::size_t n = 0; n < Next; ++n) {
+                        long double acc = Xref[m + M * (0 + ns_ref * k)].real();
+                        for (std::size_t q = 1; q < ns_ref; ++q) {
+                            auto v = Xref[m + M * (q + ns_ref * k)];
+                            long double a = tau * ((q * n) % Next) / Next;
+                            long double w = (2 * q == Next) ? 1.0L : 2.0L;
+                            acc += w * (v.real() * cosl(a) - ((2 * q == Next) ? 0.0L : v.imag() * sinl(a)));
+                        }
+                        double err = std::abs(double(want[m + M * (n + Next * k)]) - double(acc));
+                        worst = std::max(worst, err);
+                        ok = ok && err <= tol<T>(Next) * double(Next);
+                    }
+            if (!ok) std::printf("plain c2r plan %s M=%zu N=%zu differs from the direct DFT by %g\n", real, M, Next, worst);
+            CHECK(ok);
+        }
         std::size_t ndiff = 0, first = 0;
         for (std::size_t i = 0; i < got.size(); ++i) {
             if (!(got[i] == want[i])) {
@@ -356,7 +446,7 @@ int main() {
 
     // --- c2c analytic, reference size lists (test/c2c.cpp:56-59), shared jit cache
     jit_cache_all cache;
-    for (std::size_t M : {1u, 3u, 16u, 17u, 64u})
+    for (std::size_t M : {1u, 2u, 3u, 16u, 17u, 64u, 256u, 1024u})
         for (std::size_t N : {2u, 3u, 5u, 7u, 11u, 13u, 4u, 8u, 16u, 32u, 128u, 256u, 512u, 27u, 63u, 105u, 363u})
             for (std::size_t K : {1u, 32u}) {
                 c2c_analytic<float>(stream, M, N, K, &cache);
@@ -369,13 +459,40 @@ int main() {
     CHECK(cache.kernel_names().size() == cached);
     c2c_identity<float>(stream, 16, 200, 40);
     c2c_identity<double>(stream, 3, 343, 9);
+    // test/c2c.cpp:65-82 (non-packed) and :84-127 (identity)
+    for (std::size_t M : {1u, 32u}) {
+        for (std::size_t N : {6u, 17u, 102u}) {
+            c2c_nonpacked<float>(stream, M, N, 33);
+            c2c_nonpacked<double>(stream, M, N, 33);
+        }
+        for (std::size_t N : {5u, 63u, 92u}) {
+            c2c_identity_inplace<float>(stream, M, N, 16);
+            c2c_identity_inplace<double>(stream, M, N, 16);
+        }
+    }
 
-    // --- real transforms
+    // --- real transforms 1d: test/r2c.cpp:182-190 (r2c out-of-place) with the c2r mirror, :299-308 (c2r
+    // out-of-place lists), :192-200 (r2c in-place), :310-324 (c2r in-place, polluted imag(X[0]))
     for (std::size_t M : {1u, 3u, 32u})
-        for (std::size_t N : {2u, 4u, 5u, 8u, 27u, 16u, 128u, 105u, 256u, 102u, 26u}) {
+        for (std::size_t N : {2u, 4u, 5u, 8u, 27u, 16u, 32u, 128u, 105u, 256u, 512u, 102u, 220u, 10u, 26u})
+            for (std::size_t K : {1u, 33u}) {
+                r2c_c2r<float>(stream, M, N, K);
+                r2c_c2r<double>(stream, M, N, K);
+            }
+    for (std::size_t M : {1u, 5u, 32u})
+        for (std::size_t N : {11u, 16u, 25u, 96u, 256u, 300u, 315u}) {
             r2c_c2r<float>(stream, M, N, 33);
             r2c_c2r<double>(stream, M, N, 33);
         }
+    for (std::size_t M : {1u, 3u})
+        for (std::size_t N : {4u, 12u, 13u, 110u}) {
+            real_nd<float, 1>(stream, M, {N}, 65, true);
+            real_nd<double, 1>(stream, M, {N}, 65, true);
+        }
+    for (std::size_t N : {5u, 16u, 21u, 48u, 512u}) {
+        real_nd<float, 1>(stream, 1, {N}, 33, true, true);
+        real_nd<double, 1>(stream, 1, {N}, 33, true, true);
+    }
 
     // --- real 2d / 3d, the reference's case lists (test/r2c.cpp:206-252 forward, :338-372 backward)
     for (std::size_t M : {1u, 3u})
@@ -385,6 +502,19 @@ int main() {
                 real_nd<double, 2>(stream, M, N, K, true);
             }
             for (auto N : {std::array<std::size_t, 3>{4, 8, 2}, std::array<std::size_t, 3>{8, 256, 5}}) {
+                real_nd<float, 3>(stream, M, N, K, true);
+                real_nd<double, 3>(stream, M, N, K, true);
+            }
+        }
+    // c2r 2d / 3d in-place lists (test/r2c.cpp:326-346)
+    for (std::size_t M : {1u, 3u})
+        for (std::size_t K : {1u, 54u}) {
+            for (auto N : {std::array<std::size_t, 2>{4, 2}, std::array<std::size_t, 2>{96, 96}}) {
+                real_nd<float, 2>(stream, M, N, K, true);
+                real_nd<double, 2>(stream, M, N, K, true);
+            }
+            for (auto N : {std::array<std::size_t, 3>{4, 8, 2}, std::array<std::size_t, 3>{96, 96, 80}}) {
+                if (N[0] == 96 && M * K > 54) continue; // 3 x 54 x 96 x 96 x 80 reals: 1 GB per precision on the host
                 real_nd<float, 3>(stream, M, N, K, true);
                 real_nd<double, 3>(stream, M, N, K, true);
             }

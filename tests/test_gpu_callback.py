@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from callbacks import load_zero_pad_cuda, load_zero_pad_opencl, store_truncate_scale_opencl
-from common import cdtype, rdtype
+from common import TOL, rel_l2, cdtype, rdtype
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -43,10 +43,19 @@ def test_load_callback(pkg, fp, lang, M, N):
     src = (load_zero_pad_opencl if lang == "opencl" else load_zero_pad_cuda)(real, M, ns_ref, ns)
     cfg_ref = pkg.make_config(1, [M, N_ext, K], fp, pkg.BACKWARD, pkg.C2R, **strides)
     cfg = pkg.make_config(1, [M, N_ext, K], fp, pkg.BACKWARD, pkg.C2R, callbacks=(src, "load", None, lang), **strides)
-    x_ref, _ = _run(pkg, cfg_ref, X_ref.reshape(-1), np.zeros(K * N_ext * M, dtype=rdtype(fp)))
+    x_ref, ref_names = _run(pkg, cfg_ref, X_ref.reshape(-1), np.zeros(K * N_ext * M, dtype=rdtype(fp)))
     x, names = _run(pkg, cfg, X.reshape(-1), np.zeros(K * N_ext * M, dtype=rdtype(fp)))
     assert names[0].endswith("_load")
     assert np.array_equal(x, x_ref), names
+    # two plans that are wrong the same way would pass the == above (round 1: fp64 M=32 N=212 was):
+    # the plain plan is also held against an independent fp64 transform, and must reproduce itself
+    Xh = X_ref.astype(np.complex128)
+    Xh[:, 0, :] = Xh[:, 0, :].real          # imag(X[0]) is ignored by c2r (test/r2c.cpp:310-324)
+    Xh[:, ns_ref - 1, :] = Xh[:, ns_ref - 1, :].real  # zero-padded: the Nyquist row is 0 anyway
+    want = np.fft.irfft(Xh, n=N_ext, axis=1) * N_ext
+    assert rel_l2(x_ref.reshape(K, N_ext, M), want) < TOL[fp], ref_names
+    again, _ = _run(pkg, cfg_ref, X_ref.reshape(-1), np.full(K * N_ext * M, np.nan, dtype=rdtype(fp)))
+    assert np.array_equal(again, x_ref), ref_names
 
 
 @pytest.mark.parametrize("fp", [4, 8])
@@ -68,6 +77,8 @@ def test_store_callback(pkg, fp, M, N):
     want = (Y_ref.reshape(K, nspec, M)[:, :ncut, :] * rdtype(fp)(1.0 / N)).astype(cdtype(fp))
     assert names[0].endswith("_store")
     assert np.array_equal(Y.reshape(K, ncut, M), want), names
+    full = np.fft.rfft(xin.astype(np.float64).reshape(K, N, M), axis=1)
+    assert rel_l2(Y_ref.reshape(K, nspec, M), full) < TOL[fp]
 
 
 @pytest.mark.parametrize("fp,N", [(4, 64), (4, 256), (8, 64)])

@@ -19,24 +19,36 @@ def _stream():
 
 
 def _exec_bytes(pkg, cfg, x_np, out_dtype, nout, inplace):
-    """Run a plan on raw byte buffers (in-place plans view one buffer as both types)."""
+    """Run a plan on raw byte buffers (in-place plans view one buffer as both types).  Every call
+    executes the plan twice on fresh buffers and requires bit-identical results (determinism: round 1
+    shipped a kernel whose stores raced, GPUTEST_r01.json)."""
     plan = pkg.Plan(cfg, stream=_stream())
-    if inplace:
-        nbytes = max(x_np.nbytes, nout * np.dtype(out_dtype).itemsize)
-        raw = np.zeros(nbytes, np.uint8)
-        raw[: x_np.nbytes] = x_np.view(np.uint8)
-        d = torch.from_numpy(raw).cuda()
-        plan.execute(d)
-        torch.cuda.synchronize()
-        res = d.cpu().numpy().view(out_dtype)[:nout]
-    else:
-        xd = torch.from_numpy(x_np.view(np.uint8)).cuda()
-        yd = torch.zeros(nout * np.dtype(out_dtype).itemsize, dtype=torch.uint8, device="cuda")
-        plan.execute(xd, yd)
-        torch.cuda.synchronize()
-        res = yd.cpu().numpy().view(out_dtype)
+    results = []
+    for fill in (0, 0xFF):
+        if inplace:
+            nbytes = max(x_np.nbytes, nout * np.dtype(out_dtype).itemsize)
+            raw = np.zeros(nbytes, np.uint8)
+            raw[: x_np.nbytes] = x_np.view(np.uint8)
+            d = torch.from_numpy(raw).cuda()
+            plan.execute(d)
+            torch.cuda.synchronize()
+            results.append(d.cpu().numpy().view(out_dtype)[:nout])
+        else:
+            xd = torch.from_numpy(x_np.view(np.uint8)).cuda()
+            yd = torch.full((nout * np.dtype(out_dtype).itemsize,), fill, dtype=torch.uint8, device="cuda")
+            plan.execute(xd, yd)
+            torch.cuda.synchronize()
+            results.append(yd.cpu().numpy().view(out_dtype))
     names = plan.kernel_names
     plan.close()
+    res, again = results
+    if inplace:
+        assert np.array_equal(res.view(np.uint8), again.view(np.uint8)), ("second execution differs", names)
+    else:
+        # the second run started from 0xFF bytes: only the addressed elements must agree
+        same = res.view(np.uint8) == again.view(np.uint8)
+        untouched = (again.view(np.uint8) == 0xFF) & (res.view(np.uint8) == 0)
+        assert np.all(same | untouched), ("second execution differs", names)
     return res, names
 
 
@@ -161,3 +173,15 @@ def test_real_large_prime_factors_vs_oracle(pkg, oracle, fp, ttype, M, N, K):
     """r2c / c2r with a prime factor beyond the in-register butterflies (direct-DFT stage; the
     pre/post pass then runs as a separate pass), even and odd N, in- and out-of-place."""
     test_real_vs_oracle(pkg, oracle, fp, ttype, M, N, K)
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("ttype", [R2C, C2R])
+@pytest.mark.parametrize("M", [1, 3, 16, 32])
+@pytest.mark.parametrize("N", [424, 212, 318, 530, 94, 188, 111, 222, 134, 402])
+def test_real_small_radix_times_large_prime_vs_oracle(pkg, oracle, fp, ttype, M, N):
+    """Real transforms whose half length is (small radix) x (prime > 31): the fused pre/post stage
+    next to a direct-DFT stage.  N = 424 = 2 * (4 * 53) with M = 32 in fp64 is the kernel that
+    produced racing stores in round 1 (NVRTC's ptxas spilled under the register cap and
+    rematerialised an output index from a dead register); 2p, 4p, 6p, 3p, 10p shapes around it."""
+    test_real_vs_oracle(pkg, oracle, fp, ttype, M, N, 4 if M > 1 else 33)
