@@ -150,14 +150,55 @@ def run_reference_sample(steps, warmup, threads):
     return fl / dt * 1e-9, by / dt * 1e-9, dt, kind, sample
 
 
+POCKETFFT_TENSOR_BYTES = 32 << 20
+
+
+def run_pocketfft_sample(steps, warmup, threads):
+    """An honest CPU line: scipy.fft (pocketfft, C++) over ALL 210 (precision, N) shapes of the sweep,
+    same M=16 double-batched layout (transform along axis 1 of [K][N][M]), K cut so that every tensor is
+    32 MiB, `threads` workers.  Not the reference's code -- the reference has no CPU implementation of
+    this path that runs here -- but the best CPU FFT in this image."""
+    import numpy as np
+    import scipy.fft
+    rng = np.random.default_rng(0)
+    work = []
+    for fp in (4, 8):
+        dt = np.complex64 if fp == 4 else np.complex128
+        base = (rng.standard_normal(POCKETFFT_TENSOR_BYTES // (2 * fp)) +
+                1j * rng.standard_normal(POCKETFFT_TENSOR_BYTES // (2 * fp))).astype(dt)
+        for n in sweep_sizes():
+            k = max(1, POCKETFFT_TENSOR_BYTES // (M_BATCH * n * 2 * fp))
+            x = base[: k * n * M_BATCH].reshape(k, n, M_BATCH)
+            work.append((x, flops_c2c(n, M_BATCH * k), 2.0 * M_BATCH * n * k * 2 * fp))
+    def step():
+        for x, _, _ in work:
+            scipy.fft.fft(x, axis=1, workers=threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    fl = sum(w[1] for w in work)
+    by = sum(w[2] for w in work)
+    return {"value": fl / dt * 1e-9, "unit": "GFLOP/s", "cores": threads, "kind": "pocketfft", "gbs": by / dt * 1e-9,
+            "seconds_per_step": dt,
+            "sample": "scipy.fft.fft(x, axis=1, workers=%d) on all 210 (fp, N) shapes of the sweep, M=16, K cut to "
+                      "32 MiB per tensor (out-of-place, complex input resident in host memory)" % threads}
+
+
 def reference_arm(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     steps = max(1, args.steps)
-    warmup = max(1, min(args.warmup, 3))
+    warmup = max(3, args.warmup)  # same warm-up rule as the repo arm
     gf, gbs, dt, kind, sample = run_reference_sample(steps, warmup, threads)
+    try:
+        pocket = run_pocketfft_sample(2, 1, threads)
+    except Exception as ex:
+        pocket = {"value": None, "kind": "pocketfft", "error": str(ex)[:200]}
     line = {
         "impl": "reference",
         "metric": "c2c GFLOP/s (5N*log2N), 1d double-batched sweep N=2..512",
@@ -166,7 +207,14 @@ def reference_arm(args, emit=print):
         "dtype": "f32+f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "gbs": gbs,
-        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample},
+        "what_this_is": ("the reference's generated OpenCL-C kernels run work-item by work-item under a host emulator "
+                         "(oracle/_ref; the reference's real backends need an OpenCL/SYCL/Level-Zero device, SURVEY.md 8c) "
+                         "on an 11-shape sample of the sweep with K cut to CPU size: a parity-grade stand-in, NOT a tuned "
+                         "CPU FFT.  `pocketfft` beside it is the honest CPU number for the same layout."),
+        "same_config": False,
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": kind, "sample": sample,
+                         "pocketfft": pocket},
+        "pocketfft": pocket,
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,6 +225,35 @@ def workload_config(gpus):
     return {"workload": "1d c2c fp32+fp64 sweep, 105 seven-smooth N in [2,512], M=16, K=1GiB/(16*N*sizeof(complex)) per GPU, out-of-place, forward",
             "M": M_BATCH, "tensor_bytes_per_gpu": TENSOR_BYTES, "n_sizes": len(sweep_sizes()),
             "l2": "inputs_larger_than_l2 (2 GiB streamed per launch)", "parallelism": "k-sharded x%d, no collective" % gpus}
+
+
+def measure_copy_ceiling(torch, dist, world, dev, barrier, nbytes, reps=3):
+    """What the host link gives this job with no FFT at all: H2D of `nbytes` on one stream while D2H of
+    `nbytes` runs on another (pinned buffers, all ranks at once), best of `reps`.  GB/s counts both
+    directions, whole job."""
+    hin = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dout = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for _ in range(reps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        best = dt if best is None else min(best, dt)
+    return 2.0 * nbytes * world / best * 1e-9
 
 
 def measure_e2e(args, torch, dist, plans, world, dev, barrier, total_flops):
@@ -200,6 +277,9 @@ def measure_e2e(args, torch, dist, plans, world, dev, barrier, total_flops):
             nb = M_BATCH * n * k * 2 * fp
             plan.execute_host(hin[fp][: nb // fp], hout[:nb])
 
+    # untimed: the first host call creates the device ring and its streams
+    fp0, n0, k0, plan0 = plans[0]
+    plan0.execute_host(hin[fp0][: M_BATCH * n0 * k0 * 2], hout[: M_BATCH * n0 * k0 * 2 * fp0])
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
@@ -210,11 +290,19 @@ def measure_e2e(args, torch, dist, plans, world, dev, barrier, total_flops):
         t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
+    gbs = (h2d + d2h) * world / t_e2e * 1e-9
+    try:
+        ceiling = measure_copy_ceiling(torch, dist, world, dev, barrier, TENSOR_BYTES)
+    except Exception:
+        ceiling = None
     # whole-job figures, like `value`: every rank copies its own slab in and out
     return {"value": total_flops / t_e2e * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d * world,
             "d2h_bytes_per_step": d2h * world, "ms_per_step": t_e2e * 1e3, "steps": args.e2e_steps,
-            "gbs": (h2d + d2h) * world / t_e2e * 1e-9,
-            "api": "bbfft_cuda_plan_execute_host: pinned host buffers, H2D + kernel + D2H per plan, pipelined over k slabs"}
+            "gbs": gbs, "copy_ceiling_gbs": ceiling,
+            "frac_of_copy_ceiling": (gbs / ceiling if ceiling else None),
+            "copy_ceiling": "pinned 1 GiB H2D || 1 GiB D2H on two streams, every rank at once, no FFT (same units as gbs)",
+            "api": "bbfft_cuda_plan_execute_host: pinned host buffers; slabs of 16 MiB go H2D -> kernel -> D2H over a "
+                   "4-slot device ring on three streams"}
 
 
 def other_configs(peak):
@@ -254,6 +342,132 @@ def other_configs(peak):
                     "time_us": round(r["time_us"], 2), "cufft_GBs": round(r["cufft_GBs"], 1) if r["cufft_GBs"] else None,
                     "rel_l2_vs_fp64": r["err"], "launches": r["launches"]})
     return out
+
+
+def sharded_configs(torch, dist, pkg, world, rank, dev, stream, peak):
+    """BASELINE configs 3 and 5 and a strong-scaling point, timed on every rank of an N-GPU run (no
+    collective on the data path; the per-row time is the max over ranks, CUDA events on the launching
+    stream, median of 9 with the L2 flushed before every launch).
+
+    weak rows    -- every rank runs the full per-GPU problem of the config (C3: r2c/c2r fp32 N=256 M=1
+                    K=2^20 in/out of place; C5: c2c fp32 M=16 N=256 with identity load/store callbacks and
+                    one transpose_fft_transpose shape), aggregate GB/s = world * bytes / t.
+    strong rows  -- ONE ~1 GiB c2c tensor (the headline's per-GPU problem) split into `world` contiguous k
+                    slabs (128 MiB per GPU at world = 8, the smallest slab SURVEY.md 8e allows); rank 0 also
+                    times the whole tensor on its own GPU, so efficiency = t_whole / (world * t_slab)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+
+    def timed(fn, reps=9):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            bc.flush_l2()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def reduce_max(t):
+        if world == 1:
+            return t
+        v = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    rows = []
+
+    def weak_row(name, nbytes, flops, fn, launches=1):
+        if world > 1:
+            dist.barrier()
+        t = reduce_max(timed(fn))
+        rows.append({"config": name, "scaling": "weak", "time_us": round(t * 1e6, 2), "launches": launches,
+                     "GBs": round(nbytes * world / t * 1e-9, 1), "GBs_per_gpu_frac_of_peak": round(nbytes / t * 1e-9 / peak, 4),
+                     "GFLOPs": round(flops * world / t * 1e-9, 1)})
+
+    # ---- C3: r2c / c2r fp32 N=256 M=1 K=2^20, in- and out-of-place (SURVEY.md 8d)
+    N, K = 256, 1 << 20
+    nh = N // 2 + 1
+    nbytes = float(N * 4 + nh * 8) * K
+    flops = 2.5 * N * math.log2(N) * K
+    xr = torch.rand(K, N, dtype=torch.float32, device=dev)
+    spec = torch.empty(K, nh, dtype=torch.complex64, device=dev)
+    back = torch.empty(K, N, dtype=torch.float32, device=dev)
+    pad = torch.zeros(K, 2 * nh, dtype=torch.float32, device=dev)
+    for ttype, nm, src, dst in ((pkg.R2C, "r2c", xr, spec), (pkg.C2R, "c2r", spec, back)):
+        d = pkg.FORWARD if ttype == pkg.R2C else pkg.BACKWARD
+        plan = pkg.Plan(pkg.make_config(1, [1, N, K], 4, d, ttype, inplace=False), stream=stream, device=dev.index)
+        weak_row("C3 %s f32 N=256 M=1 K=2^20 out-of-place" % nm, nbytes, flops, lambda: plan.execute(src, dst))
+        plan.close()
+        plan = pkg.Plan(pkg.make_config(1, [1, N, K], 4, d, ttype, inplace=True), stream=stream, device=dev.index)
+        weak_row("C3 %s f32 N=256 M=1 K=2^20 in-place" % nm, nbytes, flops, lambda: plan.execute(pad))
+        plan.close()
+    del xr, spec, back, pad
+
+    # ---- C5: callbacks (identity load/store: the cost of the hooks) and a transpose_fft_transpose shape
+    n5 = 256
+    k5 = TENSOR_BYTES // (M_BATCH * n5 * 8)
+    x5 = torch.view_as_complex(torch.rand(k5, n5, M_BATCH, 2, dtype=torch.float32, device=dev))
+    y5 = torch.empty_like(x5)
+    cb = (bc.IDENTITY_CB % dict(v="float2"), "load", "store", "cuda")
+    for label, callbacks in (("plain", None), ("identity load/store callbacks", cb)):
+        plan = pkg.Plan(pkg.make_config(1, [M_BATCH, n5, k5], 4, pkg.FORWARD, pkg.C2C, inplace=False, callbacks=callbacks),
+                        stream=stream, device=dev.index)
+        weak_row("C5 c2c f32 M=16 N=256 K=%d %s" % (k5, label), 2.0 * x5.numel() * 8,
+                 5.0 * n5 * math.log2(n5) * M_BATCH * k5, lambda: plan.execute(x5, y5))
+        plan.close()
+    del x5, y5
+    mt, nt = 128, 512  # examples/transpose_fft_transpose/tft.cpp:20,100-103 (fp64)
+    kt = max(1, int(512e6) // (16 * mt * nt))
+    xt = torch.view_as_complex(torch.rand(kt, nt, mt, 2, dtype=torch.float64, device=dev))
+    yt = torch.empty_like(xt)
+    plan = pkg.Plan(pkg.make_config(1, [mt, nt, kt], 8, pkg.FORWARD, pkg.C2C, inplace=False), stream=stream, device=dev.index)
+    weak_row("C5 tft shape c2c f64 M=128 N=512 K=%d (double-batched plan, no transposes)" % kt, 2.0 * xt.numel() * 16,
+             5.0 * nt * math.log2(nt) * mt * kt, lambda: plan.execute(xt, yt))
+    plan.close()
+    del xt, yt
+
+    # ---- strong scaling: one 1 GiB tensor split into `world` k slabs
+    for fp, n in ((4, 64), (4, 256), (4, 512), (8, 64), (8, 490)):
+        k_total = TENSOR_BYTES // (M_BATCH * n * 2 * fp)
+        k_rank = k_total // world
+        rdt = torch.float32 if fp == 4 else torch.float64
+        x = torch.view_as_complex(torch.rand(k_total if rank == 0 else k_rank, n, M_BATCH, 2, dtype=rdt, device=dev))
+        y = torch.empty_like(x)
+        slab = pkg.Plan(pkg.make_config(1, [M_BATCH, n, k_rank], fp, pkg.FORWARD, pkg.C2C, inplace=False), stream=stream,
+                        device=dev.index)
+        if world > 1:
+            dist.barrier()
+        t_slab = reduce_max(timed(lambda: slab.execute(x, y)))
+        slab.close()
+        t_whole = None
+        if world > 1 and rank == 0:
+            whole = pkg.Plan(pkg.make_config(1, [M_BATCH, n, k_total], fp, pkg.FORWARD, pkg.C2C, inplace=False), stream=stream,
+                             device=dev.index)
+            t_whole = timed(lambda: whole.execute(x, y))
+            whole.close()
+        if world > 1:
+            dist.barrier()
+        nb = 2.0 * M_BATCH * n * k_rank * world * 2 * fp
+        row = {"config": "strong: c2c %s M=16 N=%d, K=%d total = %d per GPU (%.0f MiB in per GPU)" %
+                         ("f32" if fp == 4 else "f64", n, k_rank * world, k_rank, nb / world / 2 / (1 << 20)),
+               "scaling": "strong", "time_us": round(t_slab * 1e6, 2), "launches": 1,
+               "GBs": round(nb / t_slab * 1e-9, 1), "GBs_per_gpu_frac_of_peak": round(nb / world / t_slab * 1e-9 / peak, 4)}
+        if t_whole:
+            row["one_gpu_time_us"] = round(t_whole * 1e6, 2)
+            row["strong_efficiency"] = round(t_whole / (world * t_slab), 4)
+            # what is not bandwidth: the fixed cost of a launch (measured ~5 us back to back) in a slab that
+            # takes t_slab in total
+            row["launch_overhead_share"] = round(5e-6 / t_slab, 4)
+        rows.append(row)
+        del x, y
+    return rows
 
 
 # ------------------------------------------------------------------------------------------------
@@ -387,8 +601,13 @@ def main():
         "kernel": "bbk::fft1d<C> (all 210 instantiations of the sweep, per-launch CUDA events)",
         "algorithmic_bytes_per_launch": "2*N*sizeof(complex)*M*K = 2 GiB",
         "per_size_frac": {"min": fracs[0], "median": fracs[len(fracs) // 2], "max": fracs[-1],
-                          "n_below_0.8": sum(1 for f in fracs if f < 0.8), "statistic": "median over the timed steps"},
+                          "n_below_0.8": sum(1 for f in fracs if f < 0.8), "n_below_0.85": sum(1 for f in fracs if f < 0.85),
+                          "statistic": "median over the timed steps"},
         "worst": {"fp": worst[0], "N": worst[1], "GBs": worst[4], "kernel": worst[6]},
+        "below_0.8": [{"fp": r[0], "N": r[1], "frac": round(r[4] / peak, 4)} for r in rows if r[4] / peak < 0.8],
+        # every (precision, N) of the sweep: fraction of the measured HBM peak, median launch of the timed steps
+        "per_size": {("f32" if fp == 4 else "f64"): {str(r[1]): round(r[4] / peak, 3) for r in rows if r[0] == fp}
+                     for fp in (4, 8)},
     }
     if args.per_size and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.per_size)), exist_ok=True)
@@ -404,15 +623,30 @@ def main():
     except Exception as ex:  # keep the device-resident numbers even if the host path fails
         e2e = {"value": None, "unit": "GFLOP/s", "error": str(ex)[:300]}
 
+    sharded = None
+    if not args.no_extra:
+        try:
+            sharded = sharded_configs(torch, dist, pkg, world, rank, dev, stream, peak)
+        except Exception as ex:
+            sharded = {"error": str(ex)[:300]}
+            if world > 1:
+                raise  # a rank that left the sequence would hang the others in the next barrier
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
             try:
-                gf, cgbs, dt, kind, sample = run_reference_sample(2, 1, os.cpu_count() or 1)
-                cpu = {"value": gf, "unit": "GFLOP/s", "cores": os.cpu_count() or 1, "kind": kind,
-                       "sample": sample, "gbs": cgbs}
-            except Exception as ex:  # the checker is optional for the measurement itself
+                cpu = run_pocketfft_sample(2, 1, cores)
+            except Exception as ex:
                 cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+            try:
+                # the reference's generated kernels under the host emulator: parity-grade, kept beside it
+                gf, cgbs, dt, kind, sample = run_reference_sample(1, 1, cores)
+                cpu["reference_emulated"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+                                             "sample": sample, "gbs": cgbs}
+            except Exception as ex:  # the checker is optional for the measurement itself
+                cpu["reference_emulated"] = {"value": None, "kind": "unavailable", "sample": str(ex)[:200]}
         other = None
         if world == 1 and not args.no_extra:
             try:
@@ -429,6 +663,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * steps, "clocks": clocks,
             "other_configs": other,
+            "sharded_configs": sharded,
         }
         emit(json.dumps(line))
     for _, _, _, p in plans:

@@ -95,46 +95,102 @@ struct bbfft_cuda_plan_s {
 };
 
 namespace {
-// Device staging for the host-buffer entry point: one pair of buffers and two copy streams per
-// device, shared by all plans (grown on demand, released at process exit).
-struct staging {
+// Host-buffer entry point (bbfft_cuda_plan_execute_host): a per-device ring of device slots and three
+// streams.  Slab c of a plan goes  H2D (copy-in stream) -> kernel (compute stream) -> D2H (copy-out
+// stream), chained by events, while slab c+1 is already on its way in and slab c-1 on its way out:
+// both PCIe directions stay busy and the device footprint is SLOTS * 2 * slot bytes whatever the
+// tensor size.  Slots are handed out round-robin under a mutex that only guards the bookkeeping, so
+// concurrent callers (several plans, several host threads) interleave slab by slab instead of
+// serialising whole transforms; nothing is freed or reallocated between plans.  Plans whose k slices
+// are not contiguous byte ranges (or nd plans) take the whole-tensor path below.
+struct host_ring {
+    static constexpr int SLOTS = 4;
     std::mutex mtx;
-    void *in = nullptr, *out = nullptr;
-    size_t in_bytes = 0, out_bytes = 0;
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaEvent_t ev = nullptr;
-    void reserve(size_t need_in, size_t need_out) {
-        if (in_bytes < need_in) {
-            if (in) cudaFree(in);
-            in = nullptr;
-            in_bytes = 0;
-            BBFFT_CUDA_CHECK(cudaMalloc(&in, need_in));
-            in_bytes = need_in;
+    std::size_t slot_bytes = 0;
+    void *in[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    void *out[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t loaded[SLOTS], computed[SLOTS], drained[SLOTS];
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t entry = nullptr;
+    unsigned next = 0;
+    // whole-tensor path: grow-only buffers
+    void *whole_in = nullptr, *whole_out = nullptr;
+    std::size_t whole_in_bytes = 0, whole_out_bytes = 0;
+
+    void init(std::size_t want_slot) {
+        if (!s_in) {
+            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
+            for (int i = 0; i < SLOTS; ++i) {
+                BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&loaded[i], cudaEventDisableTiming));
+                BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+                BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+            }
         }
-        if (out_bytes < need_out) {
-            if (out) cudaFree(out);
-            out = nullptr;
-            out_bytes = 0;
-            BBFFT_CUDA_CHECK(cudaMalloc(&out, need_out));
-            out_bytes = need_out;
+        if (slot_bytes < want_slot) {
+            // first use, or a plan whose single slice exceeds the slot: drain and grow once
+            BBFFT_CUDA_CHECK(cudaStreamSynchronize(s_out));
+            for (int i = 0; i < SLOTS; ++i) {
+                if (in[i]) cudaFree(in[i]);
+                if (out[i]) cudaFree(out[i]);
+                in[i] = out[i] = nullptr;
+            }
+            slot_bytes = 0;
+            for (int i = 0; i < SLOTS; ++i) {
+                BBFFT_CUDA_CHECK(cudaMalloc(&in[i], want_slot));
+                BBFFT_CUDA_CHECK(cudaMalloc(&out[i], want_slot));
+            }
+            slot_bytes = want_slot;
         }
     }
-    void ensure_streams() {
-        if (!streams[0]) {
-            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&streams[0], cudaStreamNonBlocking));
-            BBFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&streams[1], cudaStreamNonBlocking));
-            BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    void reserve_whole(std::size_t need_in, std::size_t need_out) {
+        if (whole_in_bytes < need_in) {
+            if (whole_in) cudaFree(whole_in);
+            whole_in = nullptr;
+            whole_in_bytes = 0;
+            BBFFT_CUDA_CHECK(cudaMalloc(&whole_in, need_in));
+            whole_in_bytes = need_in;
+        }
+        if (whole_out_bytes < need_out) {
+            if (whole_out) cudaFree(whole_out);
+            whole_out = nullptr;
+            whole_out_bytes = 0;
+            BBFFT_CUDA_CHECK(cudaMalloc(&whole_out, need_out));
+            whole_out_bytes = need_out;
         }
     }
 };
-staging &staging_for(int device) {
+host_ring &ring_for(int device) {
     static std::mutex m;
-    static std::map<int, std::unique_ptr<staging>> all;
+    static std::map<int, std::unique_ptr<host_ring>> all;
     std::lock_guard<std::mutex> lock(m);
     auto &p = all[device];
-    if (!p) p = std::make_unique<staging>();
+    if (!p) p = std::make_unique<host_ring>();
     return *p;
 }
+std::size_t default_slot_bytes() {
+    // 16 MiB slabs: the un-overlapped head (first H2D) and tail (last D2H) of a 1 GiB transform are
+    // 2 of 66 pipeline steps; BBFFT_CUDA_HOST_SLOT_MB overrides
+    std::size_t mb = 16;
+    if (char const *e = std::getenv("BBFFT_CUDA_HOST_SLOT_MB")) mb = std::max(1l, std::atol(e));
+    return mb << 20;
+}
+struct device_scope {
+    int prev = -1;
+    explicit device_scope(int device) {
+        int cur = -1;
+        BBFFT_CUDA_CHECK(cudaGetDevice(&cur));
+        if (cur != device) {
+            BBFFT_CUDA_CHECK(cudaSetDevice(device));
+            prev = cur;
+        }
+    }
+    ~device_scope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 } // namespace
 
 extern "C" {
@@ -220,48 +276,72 @@ int bbfft_cuda_plan_execute_on(bbfft_cuda_plan_t plan, const void *in, void *out
 int bbfft_cuda_plan_execute_host(bbfft_cuda_plan_t plan, const void *host_in, size_t in_bytes, void *host_out,
                                  size_t out_bytes) {
     return guarded([&] {
-        cudaStream_t s = plan->impl->stream();
-        const bool inplace = host_in == host_out;
-        auto &st = staging_for(plan->device);
-        std::lock_guard<std::mutex> lock(st.mtx);
-        st.reserve(inplace ? std::max(in_bytes, out_bytes) : in_bytes, inplace ? 0 : out_bytes);
-        void *din = st.in;
-        void *dout = inplace ? st.in : st.out;
-        const std::uint64_t K = plan->impl->slices();
-        const std::size_t isl = plan->impl->in_slice_bytes(), osl = plan->impl->out_slice_bytes();
-        // Sliceable plans are pipelined over k slabs on two streams so that the H2D copy of slab
-        // c+1 overlaps the kernel and the D2H copy of slab c (PCIe is full duplex).
-        std::uint64_t chunks = 1;
-        if (K > 1 && isl > 0 && osl > 0 && K * isl <= in_bytes + isl && (in_bytes + out_bytes) > (32u << 20)) {
-            // slabs of >= 16 MiB, at most 16: the un-overlapped head (first H2D) and tail (last D2H)
-            // of the synchronous call shrink with the slab size
-            chunks = std::min<std::uint64_t>(std::min<std::uint64_t>(16, K / 2), std::max<std::size_t>(2, in_bytes >> 24));
+        auto &impl = *plan->impl;
+        if (in_bytes < impl.in_bytes_required() || out_bytes < impl.out_bytes_required()) {
+            throw bad_configuration("bbfft_cuda_plan_execute_host: host buffer smaller than the plan's tensor (" +
+                                    std::to_string(in_bytes) + " / " + std::to_string(out_bytes) + " bytes given, " +
+                                    std::to_string(impl.in_bytes_required()) + " / " +
+                                    std::to_string(impl.out_bytes_required()) + " needed)");
         }
-        if (chunks <= 1) {
+        device_scope dev(plan->device);
+        cudaStream_t s = impl.stream();
+        const bool inplace = host_in == host_out;
+        auto &ring = ring_for(plan->device);
+        const std::uint64_t K = impl.slices();
+        const std::size_t isl = impl.in_slice_bytes(), osl = impl.out_slice_bytes();
+        const std::size_t slice_max = std::max(isl, osl);
+        const bool sliceable = K > 1 && isl > 0 && osl > 0 && impl.slices_contiguous();
+        if (!sliceable || K * slice_max <= (8u << 20)) {
+            // one copy in, one launch, one copy out on the plan's stream
+            std::lock_guard<std::mutex> lock(ring.mtx);
+            ring.reserve_whole(inplace ? std::max(in_bytes, out_bytes) : in_bytes, inplace ? 0 : out_bytes);
+            void *din = ring.whole_in;
+            void *dout = inplace ? ring.whole_in : ring.whole_out;
             BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, host_in, in_bytes, cudaMemcpyHostToDevice, s));
-            plan->impl->enqueue(din, dout, s);
+            impl.enqueue(din, dout, s);
             BBFFT_CUDA_CHECK(cudaMemcpyAsync(host_out, dout, out_bytes, cudaMemcpyDeviceToHost, s));
             BBFFT_CUDA_CHECK(cudaStreamSynchronize(s));
             return;
         }
-        st.ensure_streams();
-        BBFFT_CUDA_CHECK(cudaEventRecord(st.ev, s));
-        std::uint64_t per = ((K + chunks - 1) / chunks + 1) & ~std::uint64_t(1); // even: odd-N real pairs
-        for (std::uint64_t c = 0, k0 = 0; k0 < K; ++c, k0 += per) {
-            std::uint64_t cnt = std::min(per, K - k0);
-            cudaStream_t cs = st.streams[c % 2];
-            if (c < 2) BBFFT_CUDA_CHECK(cudaStreamWaitEvent(cs, st.ev, 0));
-            std::size_t ioff = k0 * isl, ooff = k0 * osl;
-            std::size_t ib = std::min(cnt * isl, in_bytes > ioff ? in_bytes - ioff : 0);
-            std::size_t ob = std::min(cnt * osl, out_bytes > ooff ? out_bytes - ooff : 0);
-            BBFFT_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(din) + ioff, static_cast<char const *>(host_in) + ioff,
-                                             ib, cudaMemcpyHostToDevice, cs));
-            plan->impl->enqueue_slab(din, dout, k0, cnt, cs);
-            BBFFT_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(host_out) + ooff, static_cast<char *>(dout) + ooff, ob,
-                                             cudaMemcpyDeviceToHost, cs));
+        std::size_t slot = default_slot_bytes();
+        if (slice_max * 2 > slot) slot = slice_max * 2; // at least one pair of slices per slab
+        {
+            std::lock_guard<std::mutex> lock(ring.mtx);
+            ring.init(slot);
+            slot = ring.slot_bytes;
+            // everything the caller queued on the plan's stream precedes the first copy
+            BBFFT_CUDA_CHECK(cudaEventRecord(ring.entry, s));
+            BBFFT_CUDA_CHECK(cudaStreamWaitEvent(ring.s_in, ring.entry, 0));
         }
-        BBFFT_CUDA_CHECK(cudaStreamSynchronize(st.streams[0]));
-        BBFFT_CUDA_CHECK(cudaStreamSynchronize(st.streams[1]));
+        // slices per slab: even (odd-N real transforms pair the slices 2k', 2k'+1)
+        std::uint64_t per = std::max<std::uint64_t>(2, (slot / slice_max) & ~std::uint64_t(1));
+        cudaEvent_t last = nullptr;
+        for (std::uint64_t k0 = 0; k0 < K; k0 += per) {
+            const std::uint64_t cnt = std::min(per, K - k0);
+            const std::size_t ioff = k0 * isl, ooff = k0 * osl;
+            const std::size_t ib = std::min(cnt * isl, in_bytes - ioff);
+            const std::size_t ob = std::min(cnt * osl, out_bytes - ooff);
+            std::lock_guard<std::mutex> lock(ring.mtx); // one slab is issued as a unit
+            const unsigned i = ring.next++ % host_ring::SLOTS;
+            void *din = ring.in[i];
+            void *dout = inplace ? ring.in[i] : ring.out[i];
+            // the slot is free once its previous tenant has been copied out
+            BBFFT_CUDA_CHECK(cudaStreamWaitEvent(ring.s_in, ring.drained[i], 0));
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, static_cast<char const *>(host_in) + ioff, ib, cudaMemcpyHostToDevice,
+                                             ring.s_in));
+            BBFFT_CUDA_CHECK(cudaEventRecord(ring.loaded[i], ring.s_in));
+            BBFFT_CUDA_CHECK(cudaStreamWaitEvent(ring.s_k, ring.loaded[i], 0));
+            // the slab sits at the start of its slot: hand the plan base pointers such that slice k0 lands there
+            impl.enqueue_slab(static_cast<char const *>(din) - ioff, static_cast<char *>(dout) - ooff, k0, cnt, ring.s_k);
+            BBFFT_CUDA_CHECK(cudaEventRecord(ring.computed[i], ring.s_k));
+            BBFFT_CUDA_CHECK(cudaStreamWaitEvent(ring.s_out, ring.computed[i], 0));
+            BBFFT_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(host_out) + ooff, dout, ob, cudaMemcpyDeviceToHost,
+                                             ring.s_out));
+            BBFFT_CUDA_CHECK(cudaEventRecord(ring.drained[i], ring.s_out));
+            last = ring.drained[i];
+        }
+        // copies leave in issue order on the copy-out stream: the last slab's event covers this call
+        if (last) BBFFT_CUDA_CHECK(cudaStreamSynchronize(ring.s_out));
     });
 }
 

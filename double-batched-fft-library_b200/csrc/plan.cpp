@@ -177,6 +177,23 @@ static shared_handle<module_handle_t> jit_module(api const &a, std::string const
     return a.build_module(source, {"-DBBK_NO_REGCAP"});
 }
 
+// Launches go to the plan's device whatever device is current in the calling thread (the kernel
+// handle, its shared-memory attribute and the twiddle table belong to the creation device).
+struct device_guard {
+    int prev = -1;
+    explicit device_guard(int device) {
+        int cur = -1;
+        BBFFT_CUDA_CHECK(cudaGetDevice(&cur));
+        if (cur != device) {
+            BBFFT_CUDA_CHECK(cudaSetDevice(device));
+            prev = cur;
+        }
+    }
+    ~device_guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 static std::string env_tune() {
     char const *t = std::getenv("BBFFT_CUDA_TUNE");
     return t ? std::string(t) : std::string();
@@ -186,15 +203,27 @@ static std::string env_tune() {
 // 1d
 // ------------------------------------------------------------------------------------------
 fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::string const &tune)
-    : api_(std::move(a)) {
+    : api_(std::move(a)), cfg_(cfg), cache_(cache), tune_(tune.empty() ? env_tune() : tune) {
     auto prob = to_problem(cfg);
     K_ = prob.K;
     {
         std::size_t real_bytes = static_cast<std::size_t>(cfg.fp);
-        in_slice_bytes_ = std::size_t(prob.is2) * (cfg.type == transform_type::r2c ? 1 : 2) * real_bytes;
-        out_slice_bytes_ = std::size_t(prob.os2) * (cfg.type == transform_type::c2r ? 1 : 2) * real_bytes;
+        const std::size_t ie = (cfg.type == transform_type::r2c ? 1 : 2) * real_bytes;
+        const std::size_t oe = (cfg.type == transform_type::c2r ? 1 : 2) * real_bytes;
+        in_slice_bytes_ = std::size_t(prob.is2) * ie;
+        out_slice_bytes_ = std::size_t(prob.os2) * oe;
+        // rows stored per slice: N reals / N/2+1 spectrum bins on the real / complex side
+        const std::size_t n_in = cfg.type == transform_type::c2r ? prob.N / 2 + 1 : prob.N;
+        const std::size_t n_out = cfg.type == transform_type::r2c ? prob.N / 2 + 1 : prob.N;
+        const std::size_t in_slice_extent = (n_in - 1) * std::size_t(prob.is1) + prob.M;
+        const std::size_t out_slice_extent = (n_out - 1) * std::size_t(prob.os1) + prob.M;
+        contiguous_ = std::size_t(prob.is2) >= in_slice_extent && std::size_t(prob.os2) >= out_slice_extent;
+        if (prob.K > 0) {
+            in_required_ = ((prob.K - 1) * std::size_t(prob.is2) + in_slice_extent) * ie;
+            out_required_ = ((prob.K - 1) * std::size_t(prob.os2) + out_slice_extent) * oe;
+        }
     }
-    kp_ = plan_kernel_1d(prob, api_.props(), tune.empty() ? env_tune() : tune);
+    kp_ = plan_kernel_1d(prob, api_.props(), tune_);
     jit_cache_key key{kp_.identifier, api_.device_id()};
     if (cache) module_ = cache->get(key);
     if (!module_ && prob.cb_source.empty()) module_ = builtin_module(kp_.identifier, api_.device());
@@ -218,6 +247,16 @@ void fft1d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
         throw bad_configuration("The plan does not support in-place transform on the current device.");
     }
     if (k0 + count > K_) throw bad_configuration("slab exceeds the planned batch");
+    if ((kp_.p.pair_load && reinterpret_cast<std::uintptr_t>(in) % (2 * std::size_t(kp_.p.fp)) != 0) ||
+        (kp_.p.pair_store && reinterpret_cast<std::uintptr_t>(out) % (2 * std::size_t(kp_.p.fp)) != 0)) {
+        std::lock_guard<std::mutex> lock(unaligned_mtx_);
+        if (!unaligned_) {
+            unaligned_ = std::make_unique<fft1d_plan>(cfg_, api_, cache_, tune_.empty() ? "PAIR=0" : tune_ + ",PAIR=0");
+        }
+        unaligned_->enqueue_slab(in, out, k0, count, stream);
+        return;
+    }
+    device_guard guard(api_.device());
     kernel_args a;
     a.in = static_cast<char const *>(in) + k0 * in_slice_bytes_;
     a.out = static_cast<char *>(out) + k0 * out_slice_bytes_;
@@ -318,6 +357,7 @@ void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
                               cudaStream_t stream) {
     if (k0 + count > K_) throw bad_configuration("slab exceeds the planned batch");
     if (count == 0) return;
+    device_guard guard(api_.device());
     kernel_args a = {};
     a.in = static_cast<char const *>(in) + k0 * slice_bytes_;
     a.out = static_cast<char *>(out) + k0 * slice_bytes_;
@@ -454,6 +494,8 @@ nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::
     std::size_t isize = cfg.istride[dim_ + 1] * cfg.shape[dim_ + 1] * ibytes;
     std::size_t osize = cfg.ostride[dim_ + 1] * cfg.shape[dim_ + 1] * obytes;
     if (isize > osize) tmp_ = api_.create_device_buffer(isize);
+    in_required_ = isize;
+    out_required_ = osize;
 
     // Optional L2 blocking (BBFFT_CUDA_ND_BLOCK_BYTES=<bytes>, off by default): run all steps over
     // one block of outer k before moving to the next, so that later steps read what the previous
@@ -491,6 +533,14 @@ void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
     auto src = [&](std::size_t d) { return d == 0 ? in : static_cast<void const *>(tmp); };
     auto dst = [&](std::size_t d) { return d + 1 == n ? out : tmp; };
     if (chained_) {
+        // the launch number is a kernel argument and the completion counters grow monotonically: a
+        // captured launch would be replayed with a stale epoch and skip its waits
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        BBFFT_CUDA_CHECK(cudaStreamIsCapturing(stream, &cap));
+        if (cap != cudaStreamCaptureStatusNone) {
+            throw bad_configuration("a chained nd plan (BBFFT_CUDA_ND_CHAIN=1) cannot be captured in a CUDA graph");
+        }
+        device_guard guard(api_.device());
         chain_kernel_args ca = {};
         const std::size_t esz = 2 * std::size_t(chain_.steps[0].tile ? chain_.steps[0].tp.p.fp : chain_.steps[0].kp.p.fp);
         for (std::size_t d = 0; d < n; ++d) {

@@ -9,6 +9,7 @@
 
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,12 @@ class plan_base : public detail::plan_impl<event> {
     virtual void enqueue_slab(void const *, void *, std::uint64_t, std::uint64_t, cudaStream_t) {
         throw bad_configuration("plan cannot be sliced");
     }
+    // A k slice is one contiguous byte range of in_slice_bytes() / out_slice_bytes() on both sides and
+    // slices are laid out in k order (false e.g. for istride = {1, M*K, M}: k interleaved with n)
+    virtual bool slices_contiguous() const { return false; }
+    // bytes a caller's input / output buffer must span (last addressed element + 1)
+    virtual std::size_t in_bytes_required() const = 0;
+    virtual std::size_t out_bytes_required() const = 0;
     // identifiers of the kernels this plan launches (cache keys)
     virtual void kernel_names(std::vector<std::string> &names) const = 0;
     auto execute(void const *in, void *out, std::vector<event> const &dep_events) -> event override;
@@ -57,12 +64,25 @@ class fft1d_plan : public plan_base {
     std::size_t out_slice_bytes() const override { return out_slice_bytes_; }
     void enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
                       cudaStream_t stream) override;
+    bool slices_contiguous() const override { return contiguous_; }
+    std::size_t in_bytes_required() const override { return in_required_; }
+    std::size_t out_bytes_required() const override { return out_required_; }
 
   private:
+    bool contiguous_ = false;
+    std::size_t in_required_ = 0, out_required_ = 0;
     api api_;
     kernel_plan kp_;
     std::uint64_t K_ = 0;
     std::size_t in_slice_bytes_ = 0, out_slice_bytes_ = 0;
+    // M == 1 real transforms read/write the real tensor as aligned complex words; a real pointer at
+    // an odd element offset (the reference accepts it) is served by a second kernel planned with
+    // PAIR=0, created on first use
+    configuration cfg_;
+    jit_cache *cache_ = nullptr;
+    std::string tune_;
+    std::unique_ptr<fft1d_plan> unaligned_;
+    std::mutex unaligned_mtx_;
     shared_handle<module_handle_t> module_;
     cudaKernel_t kernel_ = nullptr;
     void *twiddle_ = nullptr;
@@ -87,6 +107,9 @@ class fft2d_plan : public plan_base {
     std::size_t out_slice_bytes() const override { return slice_bytes_; }
     void enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
                       cudaStream_t stream) override;
+    bool slices_contiguous() const override { return true; }
+    std::size_t in_bytes_required() const override { return slice_bytes_ * K_; }
+    std::size_t out_bytes_required() const override { return slice_bytes_ * K_; }
 
   private:
     api api_;
@@ -125,6 +148,8 @@ class nd_plan : public plan_base {
     }
     std::uint64_t k_block() const { return kblock_; }
     bool chained() const { return chained_; }
+    std::size_t in_bytes_required() const override { return in_required_; }
+    std::size_t out_bytes_required() const override { return out_required_; }
 
   private:
     api api_;
@@ -132,6 +157,7 @@ class nd_plan : public plan_base {
     std::vector<std::shared_ptr<plan_base>> plans_;
     std::vector<std::uint64_t> mult_; // slices of pass d per outer k
     std::uint64_t K_ = 0, kblock_ = 0; // outer batch and its L2 block (in k)
+    std::size_t in_required_ = 0, out_required_ = 0;
     void *tmp_ = nullptr;
     // chained execution: all steps in one persistent launch (bbk::chain)
     bool try_chain(std::vector<nd_step> const &steps, jit_cache *cache);

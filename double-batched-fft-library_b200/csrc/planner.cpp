@@ -1,6 +1,8 @@
 // planner.cpp -- see planner.hpp.
 #include "planner.hpp"
 
+#include "bbfft/api.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -220,7 +222,7 @@ stage_choice choose_stages(int N, int fp, int max_threads_per_transform, int mir
         return choose_stages(N, fp, max_threads_per_transform, 0);
     }
     if (best.radix.empty()) {
-        throw std::runtime_error("bbfft-cuda planner: no factorization found for N=" +
+        throw bad_configuration("bbfft-cuda planner: no factorization found for N=" +
                                  std::to_string(N));
     }
     return best;
@@ -432,10 +434,10 @@ char const *wisdom_special_lookup(int type, int fp, std::uint64_t n, std::uint64
 kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
                            std::string const &tune_str) {
     if (prob.N < 1 || prob.M < 1) {
-        throw std::runtime_error("bbfft-cuda planner: empty shape");
+        throw bad_configuration("bbfft-cuda planner: empty shape");
     }
     if (prob.N > 8192) {
-        throw std::runtime_error("bbfft-cuda planner: N too large for the single-kernel path");
+        throw bad_configuration("bbfft-cuda planner: N too large for the single-kernel path");
     }
     auto tune = parse_tune(tune_str);
     // stage order is the caller's when it names the radices itself or a measured real entry does
@@ -568,7 +570,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         }
     }
     p.L = int(sc.radix.size());
-    if (p.L > 4) throw std::runtime_error("bbfft-cuda planner: more than 4 stages");
+    if (p.L > 4) throw bad_configuration("bbfft-cuda planner: more than 4 stages");
     for (int s = 0; s < 4; ++s) p.radix[s] = s < p.L ? sc.radix[s] : 1;
     p.T = sc.T;
     bool has_direct = false;
@@ -606,7 +608,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     }
     p.threads = p.ML * p.T * p.BH;
     if (p.threads > dev.max_threads_per_block) {
-        throw std::runtime_error("bbfft-cuda planner: CTA too large");
+        throw bad_configuration("bbfft-cuda planner: CTA too large");
     }
 
     // ---- staging: go through shared memory whenever the direct access would be poorly coalesced
@@ -626,7 +628,9 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     if (p.mode != k_c2c) {
         // Real transforms: the spectrum side is always touched pair-wise (i, N-i) by consecutive
         // threads, which is coalesced; only the real side of an M == 1 tensor needs help.
-        const bool no_cb = prob.cb_load.empty() && prob.cb_store.empty();
+        // PAIR=0: the variant for real tensors that are not aligned to a complex word (plan.cpp)
+        const bool no_cb = prob.cb_load.empty() && prob.cb_store.empty() &&
+                           !(tune.count("PAIR") && std::atoi(tune["PAIR"].c_str()) == 0);
         p.pair_load = p.mode == k_r2c_half && prob.M == 1 && prob.is1 == 1 && prob.is2 % 2 == 0 && no_cb;
         p.pair_store = p.mode == k_c2r_half && prob.M == 1 && prob.os1 == 1 && prob.os2 % 2 == 0 && no_cb;
         p.load_staged = false;
@@ -673,7 +677,7 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
             std::string narrower = tune_str + (tune_str.empty() ? "" : ",") + "MLAUTO=1,ML=" + std::to_string(p.ML / 2);
             return plan_kernel_1d(prob, dev, narrower);
         }
-        throw std::runtime_error("bbfft-cuda planner: shared memory demand too large");
+        throw bad_configuration("bbfft-cuda planner: shared memory demand too large");
     }
     // Resident CTAs: a stage-synchronised CTA cannot overlap its own load and compute phases, so
     // ask for 2-4 CTAs per SM whenever the register cap that implies still fits the butterflies.
@@ -1043,7 +1047,7 @@ std::vector<int> tile_radices(int N, int rmax) {
             best = f;
         }
     }
-    if (best.empty()) throw std::runtime_error("bbfft-cuda planner: no tile factorization for N=" + std::to_string(N));
+    if (best.empty()) throw bad_configuration("bbfft-cuda planner: no tile factorization for N=" + std::to_string(N));
     return best;
 }
 
@@ -1197,7 +1201,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     if (tune.count("PADK")) p.PADK = std::atoi(tune["PADK"].c_str());
     p.smem_bytes = tile_smem_bytes(tile, p.PADK, p.fp);
     if (p.smem_bytes > dev.max_smem_per_block) {
-        throw std::runtime_error("bbfft-cuda planner: tile does not fit into shared memory");
+        throw bad_configuration("bbfft-cuda planner: tile does not fit into shared memory");
     }
     // resident CTAs
     {

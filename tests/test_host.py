@@ -201,3 +201,15 @@ def test_empty_batch_plans_to_an_empty_grid(pkg):
     for shape in ([0, 64, 4], [16, 0, 4]):
         with pytest.raises(pkg.BadConfiguration):
             pkg.describe(pkg.make_config(1, shape, 4, pkg.FORWARD, pkg.C2C, inplace=False))
+
+
+def test_tensor_indexer_header(tmp_path):
+    """include/bbfft/tensor_indexer.hpp against the reference's expectations (test/tensor.cpp:25-155),
+    compiled as plain host C++ (tests/cpp/test_tensor_indexer.cpp)."""
+    import subprocess
+    exe = str(tmp_path / "tti")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_tensor_indexer.cpp"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
