@@ -5,7 +5,7 @@
 // test-cufft.cpp:24-117), extended with --impl and multi-device slab sharding:
 //
 //   bbfft-bench [-i/o] [-v] [-m <M>]... [-k <K>] [-b <B>] [--impl bbfft|cufft|both]
-//               [--devices <G>] (s|d)(r|c) <N1> <N2> ...
+//               [--devices <G>] [--burst <n>] (s|d)(r|c) <N1> <N2> ...
 //
 // 1d FFT over the second mode of an M x N x K tensor; K defaults to a 1 GiB input tensor
 // (benchmark/test.hpp:18-30).  Input is the analytic single-mode signal of benchmark/signal.hpp
@@ -58,6 +58,7 @@ struct options {
     std::vector<unsigned> MM, NN;
     unsigned long K = 0;
     std::size_t bytes = std::size_t(1) << 30;
+    int burst = 0; // > 0: also time `burst` back-to-back executes between two CUDA events (launch-bound shapes)
     std::string impl = "both";
     int devices = 1;
 };
@@ -91,6 +92,7 @@ static options parse(int argc, char **argv) {
         else if (a == "-b") o.bytes = parse_bytes(need());
         else if (a == "--impl") o.impl = need();
         else if (a == "--devices") o.devices = std::stoi(need());
+        else if (a == "--burst") o.burst = std::stoi(need());
         else if (a[0] == '-') throw std::invalid_argument("unknown option " + a);
         else if (positional++ == 0) {
             o.p = a[0];
@@ -322,6 +324,30 @@ template <typename T, bool Real> static void run_case(options const &o, unsigned
         const bool ok = check();
         const double ns = bench(exec);
         emit("bbfft-cuda", ns, ok);
+        if (o.burst > 0 && slabs.size() == 1) {
+            // back-to-back executes on the stream, no host synchronisation in between: what a caller with
+            // many small, L2-resident batches sees per transform batch (BASELINE config 1)
+            auto &s0 = slabs[0];
+            cudaEvent_t e0, e1;
+            CUDA_OK(cudaEventCreate(&e0));
+            CUDA_OK(cudaEventCreate(&e1));
+            double best = 1e30;
+            for (int rep = 0; rep < 10; ++rep) {
+                CUDA_OK(cudaEventRecord(e0, s0.stream));
+                for (int i = 0; i < o.burst; ++i) {
+                    if (o.inverse) s0.plan.execute(s0.X, s0.x);
+                    else s0.plan.execute(s0.x, s0.X);
+                }
+                CUDA_OK(cudaEventRecord(e1, s0.stream));
+                CUDA_OK(cudaEventSynchronize(e1));
+                float ms = 0;
+                CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+                best = std::min(best, double(ms) * 1e6 / o.burst);
+            }
+            emit("bbfft-cuda-burst", best, ok);
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
         for (auto &s : slabs) s.plan = {};
     }
     if (o.impl == "cufft" || o.impl == "both") {

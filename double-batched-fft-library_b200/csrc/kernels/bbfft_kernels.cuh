@@ -36,19 +36,21 @@
 #define BBK_RESTRICT __restrict__
 #define BBK_GLOBAL
 #define BBK_LAUNCH_BOUNDS(t, b)
-#define BBK_MAXNREG(r)
+#define BBK_KERNEL(t, r)
 #else
 #define BBK_DEV __device__ __forceinline__
 #define BBK_HD __host__ __device__ __forceinline__
 #define BBK_CE __host__ __device__ constexpr
 #define BBK_GLOBAL __global__
 #define BBK_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
-// -DBBK_NO_REGCAP: the host rebuilds a JIT kernel without its register cap when the capped build
-// needs local memory (plan.cpp: jit_module)
+// Kernel attribute of a stub: `t` threads per CTA, at most `r` registers per thread (the planner's
+// exact cap for the planned number of resident CTAs).  -DBBK_NO_REGCAP: the host rebuilds a JIT
+// kernel without the cap when the capped build needs local memory (plan.cpp: jit_module); the
+// launch bound keeps the uncapped kernel launchable with `t` threads.
 #ifdef BBK_NO_REGCAP
-#define BBK_MAXNREG(r)
+#define BBK_KERNEL(t, r) __launch_bounds__(t)
 #else
-#define BBK_MAXNREG(r) __maxnreg__(r)
+#define BBK_KERNEL(t, r) __maxnreg__(r)
 #endif
 #define BBK_RESTRICT __restrict__
 #endif
@@ -86,6 +88,7 @@ struct args {
     u64 K;          // number of k slices handled by this launch
     u64 M;
     i64 is1, is2, os1, os2;
+    u64 pf;         // L2 prefetch distance in CTA-batches of k (tiles for the 2d kernel); 0 = off
 };
 
 template <class T> struct alignas(2 * sizeof(T)) cx {
@@ -426,11 +429,13 @@ template <class C> struct batch_index {
 #define BBK_SYNC() ::bbfft_emu::syncthreads()
 #define BBK_TID() (::bbfft_emu::thread_idx())
 #define BBK_BID() (::bbfft_emu::block_idx())
+#define BBK_NCTAS() (::bbfft_emu::grid_dim())
 #define BBK_SMEM() (::bbfft_emu::shared_mem())
 #else
 #define BBK_SYNC() __syncthreads()
 #define BBK_TID() (int(threadIdx.x))
 #define BBK_BID() (u64(blockIdx.x))
+#define BBK_NCTAS() (u64(gridDim.x))
 #define BBK_SMEM() (bbk_dyn_smem)
 extern __shared__ __align__(16) unsigned char bbk_dyn_smem[];
 #endif
@@ -1026,6 +1031,77 @@ BBK_DEV void coop_copy(BBK_SPTR(E) sm, u64 m0, u64 k0, u64 Mtot, u64 K, i64 s1, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// L2 prefetch of a FUTURE batch.  A CTA is stage-synchronised: it loads, transforms, stores, and
+// while it transforms it keeps no load in flight; with the two or three CTAs per SM that the
+// register file allows for the long transforms, HBM idles part of the time (round 1: fp64 N=490
+// at 56 % DRAM busy, warps_active 21 %).  Instead of a second shared-memory buffer per CTA (there
+// is no room: 62 KiB per batch for fp64 N=490) the CTA that starts now asks the L2 -- 126 MB, far
+// larger than a wave of batches -- to fetch the input of the batch that will run `pf` batches
+// later (about one and a half waves), with cp.async.bulk.prefetch.L2: one instruction per 4 KiB,
+// no registers, no shared memory, no completion to wait for.  The later CTA's loads then hit L2.
+// Only for inputs whose rows are contiguous inside a k slice and without a user load callback
+// (a callback may read anywhere).  Byte ranges are rounded inwards to 16 B and clamped to the
+// slices of this launch, so nothing outside the tensor is ever named.
+// ------------------------------------------------------------------------------------------
+#ifdef BBFFT_EMU
+BBK_DEV void l2_prefetch_range(const void *, u64, u64, int, int) {}
+#else
+BBK_DEV void l2_prefetch_range(const void *base, u64 lo, u64 hi, int tid, int nthreads) {
+    // bytes [lo, hi) relative to base, dealt to the WARPS of the CTA in 4 KiB pieces: the instruction
+    // takes its operands from uniform registers, so one lane per warp issues it (a per-lane address
+    // would be serialised lane by lane)
+    constexpr u64 CH = 4096;
+    if ((tid & 31) != 0) return;
+    const int warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
+    u64 p0 = reinterpret_cast<u64>(base) + lo;
+    u64 p1 = reinterpret_cast<u64>(base) + hi;
+    p0 = (p0 + 15) & ~u64(15);
+    p1 = p1 & ~u64(15);
+    for (u64 p = p0 + u64(warp) * CH; p < p1; p += u64(nwarps) * CH) {
+        const unsigned n = unsigned(p1 - p < CH ? p1 - p : CH);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(n) : "memory");
+    }
+}
+#endif
+
+template <class C> BBK_DEV void prefetch_future_batch(args const &a, u64 bid, int tid) {
+    using T = typename C::real_t;
+    using G = geom<C>;
+    constexpr bool IN_REAL = (C::MODE == R2C_HALF || C::MODE == R2C_DOUBLE);
+    constexpr bool DOUBLE = (C::MODE == R2C_DOUBLE || C::MODE == C2R_DOUBLE);
+    constexpr u64 IE = IN_REAL ? sizeof(T) : 2 * sizeof(T);
+    // rows stored per k slice on the input side
+    constexpr u64 NIN = C::MODE == C2C          ? u64(C::N)
+                        : C::MODE == R2C_HALF   ? u64(C::NREAL)
+                        : C::MODE == R2C_DOUBLE ? u64(C::N)
+                        : C::MODE == C2R_HALF   ? u64(C::N) + 1
+                                                : u64(C::N) / 2 + 1;
+    if constexpr (!C::HAS_LOAD_CALLBACK) {
+        if (a.pf == 0) return;
+        if (u64(C::is1(a)) != C::M) return; // rows of a slice are not contiguous (folds at compile time)
+        constexpr u64 MBLKS = C::KLANES ? 1 : (C::M + C::ML - 1) / C::ML;
+        constexpr u64 KPER = C::KLANES ? u64(G::B) : u64(C::BH); // kernel-k per CTA
+        const u64 part = C::KLANES ? 0 : bid % MBLKS;
+        const u64 kb = (C::KLANES ? bid : bid / MBLKS) + a.pf; // the future batch of k
+        const u64 sl = DOUBLE ? 2 : 1;                          // user slices per kernel-k
+        const u64 uk0 = kb * KPER * sl;
+        if (uk0 >= a.K) return;
+        const u64 uk1 = uk0 + KPER * sl < a.K ? uk0 + KPER * sl : a.K;
+        const u64 slice_bytes = NIN * C::M * IE, stride_bytes = u64(C::is2(a)) * IE;
+        if (stride_bytes == slice_bytes) {
+            // packed slices: one range for the whole batch, one part per m-block CTA
+            const u64 lo = uk0 * stride_bytes, len = (uk1 - uk0) * stride_bytes;
+            l2_prefetch_range(a.in, lo + len * part / MBLKS, lo + len * (part + 1) / MBLKS, tid, G::THREADS);
+        } else {
+            for (u64 uk = uk0; uk < uk1; ++uk) {
+                const u64 lo = uk * stride_bytes;
+                l2_prefetch_range(a.in, lo + slice_bytes * part / MBLKS, lo + slice_bytes * (part + 1) / MBLKS, tid, G::THREADS);
+            }
+        }
+    }
+}
+
 // the work of CTA `bid` of the 1d kernel's grid
 template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
     using T = typename C::real_t;
@@ -1050,6 +1126,7 @@ template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
         k = k0 + bh;
     }
     const bool ok = (m < C::M) && (k < a.K);
+    prefetch_future_batch<C>(a, bid, tid);
 
     if constexpr (C::MODE == C2C) {
         constexpr int SRC0 = C::LOAD_STAGED ? IO_SMEM : IO_GLOBAL;
@@ -1274,7 +1351,23 @@ template <class C> BBK_DEV void fft1d_cta(args const &a, const u64 bid) {
     }
 }
 
-template <class C> BBK_DEV void fft1d(args const &a) { fft1d_cta<C>(a, BBK_BID()); }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may be scheduled while its predecessor on the stream is still running; it must not touch
+// global memory before griddepcontrol.wait (= predecessor complete and flushed).  Letting the next
+// launch's CTAs become resident early takes the launch latency (~1-2 us) off the critical path of
+// back-to-back executes of small, L2-resident batches (BASELINE config 1).  Without the launch
+// attribute both instructions are no-ops.
+BBK_DEV void pdl_prologue() {
+#ifndef BBFFT_EMU
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <class C> BBK_DEV void fft1d(args const &a) {
+    pdl_prologue();
+    fft1d_cta<C>(a, BBK_BID());
+}
 
 // ------------------------------------------------------------------------------------------
 // Fused 2d c2c transform ("tile kernel").  One CTA owns one M x N1 x N2 tile -- contiguous in
@@ -1295,6 +1388,27 @@ template <class C> BBK_DEV void fft1d(args const &a) { fft1d_cta<C>(a, BBK_BID()
 // ------------------------------------------------------------------------------------------
 enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2 };
 
+// Asynchronous global -> shared copies (cp.async, one element per instruction: the padded tile
+// layout puts every element at its own 8- / 16-byte aligned slot).  The copy engine of the SM moves
+// the data while the issuing warps go on computing; cp.async.wait_group + a CTA barrier publish it.
+#ifdef BBFFT_EMU
+template <class SP, class E> BBK_DEV void async_copy_elem(SP sm, int phys, const E *src) { sm[phys] = *src; }
+BBK_DEV void async_commit() {}
+BBK_DEV void async_wait_all() {}
+#else
+template <class E> BBK_DEV void async_copy_elem(E *sm, int phys, const E *src) {
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(sm + phys));
+    if constexpr (sizeof(E) == 8) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+        static_assert(sizeof(E) == 16, "complex<float> or complex<double>");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+}
+BBK_DEV void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+BBK_DEV void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
 template <class C> BBK_DEV int tile_phys(int lin) {
     if constexpr (C::PADK > 0) {
         return lin + lin / C::PADK;
@@ -1309,8 +1423,16 @@ template <class P> BBK_CE int pass_ns(int s) {
     return n;
 }
 
-template <class C, class P, int S, int SRC, int DST>
-BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid) {
+// `after_loads` runs when every thread of the CTA holds its inputs of the stage in registers; the
+// persistent tile kernel passes a hook (preceded by a barrier) that starts the asynchronous load of
+// the NEXT tile into the shared memory this tile no longer needs.
+struct no_hook {
+    static constexpr bool active = false;
+    BBK_DEV void operator()() const {}
+};
+
+template <class C, class P, int S, int SRC, int DST, class HOOK = no_hook>
+BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK after_loads = HOOK{}) {
     using T = typename C::real_t;
     constexpr int R = P::radix(S);
     constexpr int NS = pass_ns<P>(S);
@@ -1344,6 +1466,11 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
     });
     if constexpr (DST == T_SMEM_SORTED && SRC != T_GLOBAL) {
         BBK_SYNC(); // every read of the stage happens before its out-of-place writes
+    }
+    if constexpr (HOOK::active) {
+        static_assert(SRC == T_SMEM && DST == T_GLOBAL, "the hook belongs to the stage that empties shared memory");
+        BBK_SYNC(); // the tile has left shared memory
+        after_loads();
     }
     static_for<0, CNT>([&](auto ii) {
         constexpr int i = decltype(ii)::value;
@@ -1381,16 +1508,20 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
     });
 }
 
-template <class C, class P, int S, int SRC0, int DSTL>
-BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid) {
+template <class C, class P, int S, int SRC0, int DSTL, class HOOK = no_hook>
+BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK last_hook = HOOK{}) {
     if constexpr (S < P::L) {
         constexpr int SRC = (S == 0) ? SRC0 : T_SMEM;
         constexpr int DST = (S == P::L - 1) ? DSTL : T_SMEM;
         if constexpr (S > 0) {
             BBK_SYNC();
         }
-        tile_stage<C, P, S, SRC, DST>(a, sm, gbase, tid);
-        tile_pass<C, P, S + 1, SRC0, DSTL>(a, sm, gbase, tid);
+        if constexpr (S == P::L - 1 && HOOK::active) {
+            tile_stage<C, P, S, SRC, DST, HOOK>(a, sm, gbase, tid, last_hook);
+        } else {
+            tile_stage<C, P, S, SRC, DST>(a, sm, gbase, tid);
+        }
+        tile_pass<C, P, S + 1, SRC0, DSTL, HOOK>(a, sm, gbase, tid, last_hook);
     }
 }
 
@@ -1399,15 +1530,68 @@ template <class C> BBK_DEV void fft2d_tile_cta(args const &a, const u64 tile) {
     BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
     const int tid = BBK_TID();
     const u64 gbase = tile * u64(C::TILE_STRIDE);
+    if (a.pf != 0 && tile + a.pf < a.K) {
+        // the tile that runs `pf` tiles later (same reasoning as prefetch_future_batch: one 128 KiB tile
+        // per SM leaves no second CTA to overlap with; the L2 takes the role of the second buffer)
+        constexpr u64 TB = u64(C::TILE_STRIDE) * 2 * sizeof(T);
+        l2_prefetch_range(a.in, (tile + a.pf) * TB, (tile + a.pf + 1) * TB, tid, C::THREADS);
+    }
     tile_pass<C, typename C::PA, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, gbase, tid);
     BBK_SYNC();
     tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL>(a, sm, gbase, tid);
 }
 
+// Persistent variant with an asynchronous tile pipeline (C::PERSIST; grid = resident CTAs).  A CTA
+// walks the tiles bid, bid + grid, ...  The last stage of pass B pulls its inputs into registers;
+// from that barrier on the shared-memory tile is dead, so the CTA issues the cp.async copies of its
+// NEXT tile and only then computes the last butterflies and stores the finished tile: the HBM read
+// of tile i+1 overlaps the arithmetic and the HBM write of tile i, inside one CTA -- which is what a
+// 128 KiB tile (one CTA per SM, nobody else to overlap with) was missing in round 1 (0.65 of the
+// HBM peak for 2d fp32 128 x 128).  Pass A then starts from shared memory instead of global memory.
+template <class C> struct tile_loader {
+    static constexpr bool active = true;
+    using T = typename C::real_t;
+    args const &a;
+    BBK_SPTR(cx<T>) sm;
+    u64 tile; // the tile to fetch (>= a.K: nothing)
+    int tid;
+    BBK_DEV void operator()() const {
+        if (tile < a.K) {
+            const cx<T> *BBK_RESTRICT src = reinterpret_cast<const cx<T> *>(a.in) + tile * u64(C::TILE_STRIDE);
+            constexpr int TILE = C::PA::S * C::PA::N * C::PA::O;
+            for (int lin = tid; lin < TILE; lin += C::THREADS) async_copy_elem(sm, tile_phys<C>(lin), src + lin);
+        }
+        async_commit();
+    }
+};
+
+template <class C> BBK_DEV void fft2d_tile_persistent(args const &a) {
+    using T = typename C::real_t;
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const u64 step = BBK_NCTAS();
+    u64 tile = BBK_BID();
+    tile_loader<C>{a, sm, tile, tid}();
+    for (; tile < a.K; tile += step) {
+        const u64 gbase = tile * u64(C::TILE_STRIDE);
+        async_wait_all();
+        BBK_SYNC(); // every thread's copies have landed
+        tile_pass<C, typename C::PA, 0, T_SMEM, T_SMEM_SORTED>(a, sm, gbase, tid);
+        BBK_SYNC();
+        tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL, tile_loader<C>>(a, sm, gbase, tid,
+                                                                            tile_loader<C>{a, sm, tile + step, tid});
+    }
+}
+
 template <class C> BBK_DEV void fft2d_tile(args const &a) {
-    const u64 tile = BBK_BID();
-    if (tile >= a.K) return;
-    fft2d_tile_cta<C>(a, tile);
+    pdl_prologue();
+    if constexpr (C::PERSIST) {
+        fft2d_tile_persistent<C>(a);
+    } else {
+        const u64 tile = BBK_BID();
+        if (tile >= a.K) return;
+        fft2d_tile_cta<C>(a, tile);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1439,13 +1623,11 @@ struct chain_args {
 enum : int { STEP_FFT1D = 0, STEP_TILE = 1 };
 
 #ifdef BBFFT_EMU
-#define BBK_NCTAS() (::bbfft_emu::grid_dim())
 BBK_DEV void chain_wait(u64 const *p, u64 target) {
     if (*p < target) ::bbfft_emu::fail(); // one emulated CTA runs the items in order: never waits
 }
 BBK_DEV void chain_signal(u64 *p) { *p += 1; }
 #else
-#define BBK_NCTAS() (u64(gridDim.x))
 BBK_DEV void chain_wait(u64 const *p, u64 target) {
     const volatile u64 *vp = p;
     long long t0 = 0;

@@ -194,6 +194,23 @@ struct device_guard {
     }
 };
 
+// L2 prefetch distance (bbk::prefetch_future_batch): the CTA that starts now prefetches the input of
+// the batch `waves` waves of resident CTAs later.  OFF by default: measured on the B200 over the
+// 210-kernel sweep (profiles/r02d_prefetch.txt) it loses -- 0.948 of the HBM peak without, 0.913 at
+// one wave, 0.811 at 1.5, 0.72 at 2.5 (kernels that already saturate HBM pay for lines that are
+// evicted before use and fetched twice) -- and the sizes below 0.8 are not waiting for memory.
+// BBFFT_CUDA_PREFETCH_WAVES=<w> switches it on (some latency-bound kernels gain: c2r M=16 N=256 +11..17 %).
+static std::uint64_t prefetch_distance(api const &a, cudaKernel_t k, int threads, std::size_t smem_bytes,
+                                       int planned_blocks, std::uint64_t ctas_per_batch) {
+    double waves = 0.0;
+    if (char const *e = std::getenv("BBFFT_CUDA_PREFETCH_WAVES")) waves = std::atof(e);
+    if (waves <= 0.0) return 0;
+    int per_sm = a.max_active_ctas_per_sm(k, threads, smem_bytes);
+    if (per_sm < 1) per_sm = std::max(1, planned_blocks);
+    const double resident = double(per_sm) * double(a.props().sm_count);
+    return std::max<std::uint64_t>(1, std::uint64_t(waves * resident / double(std::max<std::uint64_t>(1, ctas_per_batch)) + 0.5));
+}
+
 static std::string env_tune() {
     char const *t = std::getenv("BBFFT_CUDA_TUNE");
     return t ? std::string(t) : std::string();
@@ -233,6 +250,8 @@ fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::s
     }
     kernel_ = api_.create_kernel(module_.get(), kp_.identifier, kp_.p.smem_bytes);
     twiddle_ = api_.create_twiddle_table(kp_.twiddle, kp_.p.fp);
+    prefetch_ = prefetch_distance(api_, kernel_, kp_.p.threads, kp_.p.smem_bytes, kp_.p.min_blocks,
+                                  kp_.p.klanes ? 1 : (kp_.p.M + kp_.p.ML - 1) / kp_.p.ML);
 }
 
 fft1d_plan::~fft1d_plan() { api_.release_buffer(twiddle_); }
@@ -267,10 +286,12 @@ void fft1d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
     a.is2 = kp_.p.is2;
     a.os1 = kp_.p.os1;
     a.os2 = kp_.p.os2;
+    a.pf = prefetch_;
     api_.launch_kernel(kernel_, kp_.p.grid(count), kp_.p.threads, kp_.p.smem_bytes, a, stream);
 }
 
 auto plan_base::execute(void const *in, void *out, std::vector<event> const &dep_events) -> event {
+    device_guard guard(device()); // the stream, the returned event and the launch belong to the plan's device
     cudaStream_t s = stream();
     for (auto const &e : dep_events) {
         if (e) BBFFT_CUDA_CHECK(cudaStreamWaitEvent(s, e.native(), 0));
@@ -347,6 +368,12 @@ fft2d_plan::fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::str
     }
     kernel_ = api_.create_kernel(module_.get(), tp_.identifier, tp_.p.smem_bytes);
     twiddle_ = api_.create_twiddle_table(tp_.twiddle, tp_.p.fp);
+    prefetch_ = prefetch_distance(api_, kernel_, tp_.p.threads, tp_.p.smem_bytes, tp_.p.min_blocks, 1);
+    {
+        int per_sm = api_.max_active_ctas_per_sm(kernel_, tp_.p.threads, tp_.p.smem_bytes);
+        if (per_sm < 1) per_sm = std::max(1, tp_.p.min_blocks);
+        resident_ctas_ = std::uint64_t(per_sm) * std::uint64_t(api_.props().sm_count);
+    }
 }
 
 fft2d_plan::~fft2d_plan() { api_.release_buffer(twiddle_); }
@@ -364,6 +391,12 @@ void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
     a.tw = twiddle_;
     a.K = count;
     a.M = tp_.p.M;
+    a.pf = tp_.p.persistent ? 0 : prefetch_;
+    // the persistent kernel walks the tiles with a grid of resident CTAs
+    if (tp_.p.persistent) {
+        api_.launch_kernel(kernel_, std::min<std::uint64_t>(count, resident_ctas_), tp_.p.threads, tp_.p.smem_bytes, a, stream);
+        return;
+    }
     api_.launch_kernel(kernel_, count, tp_.p.threads, tp_.p.smem_bytes, a, stream);
 }
 
@@ -550,6 +583,7 @@ void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
             ca.step[d].tw = static_cast<char const *>(chain_tw_) + std::size_t(sp.tw_offset) * esz;
             ca.step[d].K = mult_[d] * K_;
             ca.step[d].M = sp.tile ? sp.tp.p.M : sp.kp.p.M;
+            ca.step[d].pf = 0;
         }
         ca.done = static_cast<unsigned long long *>(chain_done_);
         ca.epoch = ++chain_epoch_;

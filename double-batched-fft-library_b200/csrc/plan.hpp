@@ -26,6 +26,7 @@ class plan_base : public detail::plan_impl<event> {
     // stream-ordered launch without event bookkeeping (used by the C ABI and by nd plans)
     virtual void enqueue(void const *in, void *out, cudaStream_t stream) = 0;
     virtual cudaStream_t stream() const = 0;
+    virtual int device() const = 0;
     virtual unsigned launches_per_execute() const = 0;
     // Slab interface for host-side pipelining / sharding: number of independent k slices, the
     // byte extent of one slice in the input/output tensor (0 = not sliceable), and a launch over
@@ -56,6 +57,7 @@ class fft1d_plan : public plan_base {
 
     void enqueue(void const *in, void *out, cudaStream_t stream) override;
     cudaStream_t stream() const override { return api_.stream(); }
+    int device() const override { return api_.device(); }
     unsigned launches_per_execute() const override { return 1; }
     kernel_plan const &kernel() const { return kp_; }
     void kernel_names(std::vector<std::string> &names) const override { names.push_back(kp_.identifier); }
@@ -86,6 +88,7 @@ class fft1d_plan : public plan_base {
     shared_handle<module_handle_t> module_;
     cudaKernel_t kernel_ = nullptr;
     void *twiddle_ = nullptr;
+    std::uint64_t prefetch_ = 0; // L2 prefetch distance in CTA-batches of k (bbk::args::pf)
 };
 
 // Fused 2d c2c plan: one launch of bbk::fft2d_tile, one CTA per M x N1 x N2 tile held in shared
@@ -99,6 +102,7 @@ class fft2d_plan : public plan_base {
 
     void enqueue(void const *in, void *out, cudaStream_t stream) override;
     cudaStream_t stream() const override { return api_.stream(); }
+    int device() const override { return api_.device(); }
     unsigned launches_per_execute() const override { return 1; }
     tile_plan const &kernel() const { return tp_; }
     void kernel_names(std::vector<std::string> &names) const override { names.push_back(tp_.identifier); }
@@ -119,6 +123,8 @@ class fft2d_plan : public plan_base {
     shared_handle<module_handle_t> module_;
     cudaKernel_t kernel_ = nullptr;
     void *twiddle_ = nullptr;
+    std::uint64_t prefetch_ = 0; // L2 prefetch distance in tiles
+    std::uint64_t resident_ctas_ = 1; // grid of the persistent tile kernel
 };
 
 // One step of a 2d/3d decomposition: either a fused tile launch over dims (1,2) or a
@@ -140,6 +146,7 @@ class nd_plan : public plan_base {
 
     void enqueue(void const *in, void *out, cudaStream_t stream) override;
     cudaStream_t stream() const override { return api_.stream(); }
+    int device() const override { return api_.device(); }
     unsigned launches_per_execute() const override;
     std::vector<std::shared_ptr<plan_base>> const &passes() const { return plans_; }
     void kernel_names(std::vector<std::string> &names) const override {

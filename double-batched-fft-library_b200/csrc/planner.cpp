@@ -644,8 +644,10 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
         }
     }
     // user callbacks see every element exactly once in either path, so staging stays legal.
-    if (tune.count("LD")) p.load_staged = std::atoi(tune["LD"].c_str()) != 0;
-    if (tune.count("ST")) p.store_staged = std::atoi(tune["ST"].c_str()) != 0;
+    // (real transforms stage whole aligned complex words: only for M == 1)
+    const bool stage_override_ok = p.mode == k_c2c || prob.M == 1;
+    if (tune.count("LD") && stage_override_ok) p.load_staged = std::atoi(tune["LD"].c_str()) != 0;
+    if (tune.count("ST") && stage_override_ok) p.store_staged = std::atoi(tune["ST"].c_str()) != 0;
     // Real pre/post pass: fused into the first/last stage (a thread runs a sub-FFT and its mirror,
     // no extra trip through shared memory) when the batch lanes walk m.  With t-lanes (M == 1) the
     // mirrored units leave half of every warp idle in the stage that issues the global loads;
@@ -1005,11 +1007,12 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
            << vec << " *>(out), off, r);\n    }\n";
         os << "    static BBK_DEV void str(void *, bbk::u64, real_t) {}\n";
     }
+    os << "    static constexpr bool HAS_LOAD_CALLBACK = " << (p.cb_load.empty() ? "false" : "true") << ";\n";
     os << "    static constexpr bool HAS_CALLBACKS = "
        << ((p.cb_load.empty() && p.cb_store.empty()) ? "false" : "true") << ";\n";
     os << "};\n} // namespace stub_" << identifier << "\n";
     if (!p.chained) {
-        os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") "
+        os << "extern \"C\" BBK_GLOBAL void BBK_KERNEL(" << p.threads << ", " << p.max_regs << ") "
            << identifier << "(bbk::args a) {\n    bbk::fft1d<stub_" << identifier << "::C>(a);\n}\n";
     }
     os << "#ifdef BBFFT_OCL_COMPAT\n#undef float2\n#undef double2\n#undef BBFFT_OCL_COMPAT\n#endif\n";
@@ -1216,6 +1219,10 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
     p.max_regs = reg_cap(p.threads, p.min_blocks);
     p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
+    // persistent grid + asynchronous load of the next tile (PS=0 / BBFFT_CUDA_TILE_ASYNC=0: one tile per CTA)
+    p.persistent = !p.chained;
+    if (char const *e = std::getenv("BBFFT_CUDA_TILE_ASYNC")) p.persistent = p.persistent && *e != '0';
+    if (tune.count("PS")) p.persistent = !p.chained && std::atoi(tune["PS"].c_str()) != 0;
 
     // identifier
     {
@@ -1227,6 +1234,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         for (int s = 0; s < p.b.L; ++s) os << (s ? "x" : "") << p.b.radix[s];
         os << "_th" << p.threads << "_mb" << p.min_blocks << "_pk" << p.PADK << "_ts" << p.tile_stride;
         if (p.chained) os << "_ch";
+        if (p.persistent) os << "_ps";
         plan.identifier = os.str();
     }
     // twiddles: pass A stages, then pass B stages (same construction as the 1d table)
@@ -1285,6 +1293,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         emit_pass("PassB", p.b, off_b);
         os << "struct C {\n    using real_t = " << real << ";\n    using PA = PassA;\n    using PB = PassB;\n";
         os << "    static constexpr int DIR = " << p.dir << ", THREADS = " << p.threads << ", PADK = " << p.PADK
+           << ";\n    static constexpr bool PERSIST = " << (p.persistent ? "true" : "false")
            << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull;\n";
         if (p.chained) {
             os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
@@ -1297,7 +1306,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
               "        reinterpret_cast<bbk::cx<real_t> *>(out)[off] = v;\n    }\n";
         os << "};\n} // namespace stub_" << plan.identifier << "\n";
         if (!p.chained) {
-            os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << p.max_regs << ") " << plan.identifier
+            os << "extern \"C\" BBK_GLOBAL void BBK_KERNEL(" << p.threads << ", " << p.max_regs << ") " << plan.identifier
                << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
         }
         plan.source = os.str();
@@ -1423,7 +1432,7 @@ bool plan_chain(std::vector<chain_step_problem> const &steps, device_props const
            << sp.per_k << "ull;\n};\n";
     }
     os << "} // namespace chain_" << out.identifier << "\n";
-    os << "extern \"C\" BBK_GLOBAL void BBK_MAXNREG(" << out.max_regs << ") " << out.identifier
+    os << "extern \"C\" BBK_GLOBAL void BBK_KERNEL(" << out.threads << ", " << out.max_regs << ") " << out.identifier
        << "(bbk::chain_args ca) {\n    bbk::chain<" << out.steps.size() << ", chain_" << out.identifier << "::S0, chain_"
        << out.identifier << "::S1, chain_" << out.identifier << "::S2>(ca);\n}\n";
     out.entry_source = os.str();

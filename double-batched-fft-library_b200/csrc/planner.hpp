@@ -101,6 +101,7 @@ struct tile_params {
     std::uint64_t M = 1, N1 = 1, N2 = 1, tile_stride = 0;
     tile_pass_params a, b; // axis n1, axis n2
     int threads = 256, PADK = 0, min_blocks = 1, max_regs = 255;
+    bool persistent = false; // persistent grid with the asynchronous tile pipeline (bbk::fft2d_tile_persistent)
     std::size_t smem_bytes = 0;
     bool chained = false; // see kernel_params::chained
 };

@@ -17,6 +17,8 @@
 #include <iterator>
 #include <mutex>
 #include <sstream>
+#include <utility>
+#include <vector>
 
 namespace bbfft::cuda {
 
@@ -305,11 +307,50 @@ namespace bbfft::cuda {
 // ------------------------------------------------------------------------------------------
 // event
 // ------------------------------------------------------------------------------------------
+// Every execute returns an event (the reference's plans return sycl / cl events).  Creating and
+// destroying a CUDA event per launch costs about as much as the launch itself, so retired events go
+// back to a per-device free list (launch-bound callers: BASELINE config 1).
+namespace {
+struct event_pool {
+    std::mutex mtx;
+    std::vector<std::pair<int, cudaEvent_t>> free_list;
+    cudaEvent_t take(int device) {
+        {
+            std::lock_guard<std::mutex> lock(mtx);
+            for (std::size_t i = free_list.size(); i-- > 0;) {
+                if (free_list[i].first == device) {
+                    cudaEvent_t e = free_list[i].second;
+                    free_list[i] = free_list.back();
+                    free_list.pop_back();
+                    return e;
+                }
+            }
+        }
+        cudaEvent_t e = nullptr;
+        BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return e;
+    }
+    void give(int device, cudaEvent_t e) {
+        std::lock_guard<std::mutex> lock(mtx);
+        if (free_list.size() < 256) {
+            free_list.emplace_back(device, e);
+        } else {
+            cudaEventDestroy(e);
+        }
+    }
+};
+event_pool &events() {
+    static event_pool *p = new event_pool(); // leaked on purpose: events may be retired during exit
+    return *p;
+}
+} // namespace
+
 event::event(cudaStream_t stream) {
-    cudaEvent_t e = nullptr;
-    BBFFT_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ev_ = std::shared_ptr<cudaEvent_t>(new cudaEvent_t(e), [](cudaEvent_t *p) {
-        if (*p) cudaEventDestroy(*p);
+    int device = 0;
+    BBFFT_CUDA_CHECK(cudaGetDevice(&device));
+    cudaEvent_t e = events().take(device);
+    ev_ = std::shared_ptr<cudaEvent_t>(new cudaEvent_t(e), [device](cudaEvent_t *p) {
+        if (*p) events().give(device, *p);
         delete p;
     });
     BBFFT_CUDA_CHECK(cudaEventRecord(e, stream));
@@ -367,6 +408,16 @@ cudaKernel_t api::create_kernel(module_handle_t mod, std::string const &name, st
     return k;
 }
 
+// BBFFT_CUDA_PDL=1: launches carry the programmatic-stream-serialization attribute (see
+// bbk::pdl_prologue in the device header)
+static bool pdl_enabled() {
+    static const bool on = [] {
+        char const *e = std::getenv("BBFFT_CUDA_PDL");
+        return e && *e == '1';
+    }();
+    return on;
+}
+
 void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
                         kernel_args const &args, cudaStream_t stream) const {
     if (grid == 0) return;
@@ -375,6 +426,20 @@ void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::si
     }
     kernel_args a = args;
     void *params[] = {&a};
+    if (pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(grid));
+        cfg.blockDim = dim3(unsigned(threads));
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        BBFFT_CUDA_CHECK(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void *>(k), params));
+        return;
+    }
     BBFFT_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void *>(k), dim3(unsigned(grid)),
                                       dim3(unsigned(threads)), params, smem_bytes, stream));
 }

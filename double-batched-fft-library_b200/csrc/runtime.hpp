@@ -26,6 +26,7 @@ struct kernel_args { // must match bbk::args
     unsigned long long K;
     unsigned long long M;
     long long is1, is2, os1, os2;
+    unsigned long long pf;
 };
 
 struct chain_kernel_args { // must match bbk::chain_args

@@ -25,7 +25,7 @@ pkg = importlib.import_module("double-batched-fft-library_b200")
 class Args(C.Structure):
     _fields_ = [("inp", C.c_void_p), ("out", C.c_void_p), ("tw", C.c_void_p), ("K", C.c_ulonglong),
                 ("M", C.c_ulonglong), ("is1", C.c_longlong), ("is2", C.c_longlong), ("os1", C.c_longlong),
-                ("os2", C.c_longlong)]
+                ("os2", C.c_longlong), ("pf", C.c_ulonglong)]
 
 
 RACECHECK = os.environ.get("BBFFT_EMU_RACECHECK", "0") == "1"

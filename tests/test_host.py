@@ -105,10 +105,10 @@ def test_register_cap_models_the_four_register_file_partitions(pkg):
     the per-partition register model -- 7-warp CTAs at 136 registers only fit once per SM although
     2 x 224 x 136 < 65536 (measured: the 2x slowdown of profiles/r01b_*)."""
     d = pkg.describe(pkg.make_config(1, [16, 135, 64], 8, inplace=False), "R=9x15,T=9,ML=8,BH=3,MB=2")
-    m = re.search(r"BBK_MAXNREG\((\d+)\)", d["source"])
+    m = re.search(r"BBK_KERNEL\(\d+, (\d+)\)", d["source"])
     assert m and int(m.group(1)) == 128 and d["threads"] == 216
     d = pkg.describe(pkg.make_config(1, [16, 135, 64], 8, inplace=False), "R=9x15,T=9,ML=8,BH=3,MB=1")
-    assert int(re.search(r"BBK_MAXNREG\((\d+)\)", d["source"]).group(1)) == 255
+    assert int(re.search(r"BBK_KERNEL\(\d+, (\d+)\)", d["source"]).group(1)) == 255
 
 
 def test_builtin_bundle_meets_planned_occupancy(pkg):
