@@ -378,7 +378,7 @@ int bbfft_cuda_describe(const bbfft_cuda_config *cfg, const char *tune, bbfft_cu
             desc->twiddle_len = tp.twiddle.size();
             desc->twiddle = static_cast<double *>(std::malloc(sizeof(double) * tp.twiddle.size()));
             std::memcpy(desc->twiddle, tp.twiddle.data(), sizeof(double) * tp.twiddle.size());
-            desc->grid = steps[0].tile.K;
+            desc->grid = steps[0].tile.K * std::uint64_t(tp.p.cluster);
             desc->threads = tp.p.threads;
             desc->smem_bytes = tp.p.smem_bytes;
             desc->fp = tp.p.fp;
@@ -416,7 +416,7 @@ int bbfft_cuda_describe_chain(const bbfft_cuda_config *cfg, bbfft_cuda_chain_des
         std::memset(desc, 0, sizeof(*desc));
         auto c = to_cpp(*cfg);
         if (c.dim < 2) throw bad_configuration("bbfft_cuda_describe_chain handles 2d and 3d configurations");
-        auto steps = cuda::nd_decompose(c, cuda::device_props{});
+        auto steps = cuda::nd_decompose(c, cuda::device_props{}, true);
         std::vector<cuda::chain_step_problem> probs;
         for (auto const &s : steps) {
             cuda::chain_step_problem q;

@@ -37,6 +37,7 @@
 #define BBK_GLOBAL
 #define BBK_LAUNCH_BOUNDS(t, b)
 #define BBK_KERNEL(t, r)
+#define BBK_CLUSTER(n)
 #else
 #define BBK_DEV __device__ __forceinline__
 #define BBK_HD __host__ __device__ __forceinline__
@@ -52,6 +53,7 @@
 #else
 #define BBK_KERNEL(t, r) __maxnreg__(r)
 #endif
+#define BBK_CLUSTER(n) __cluster_dims__(n, 1, 1)
 #define BBK_RESTRICT __restrict__
 #endif
 
@@ -1386,7 +1388,34 @@ template <class C> BBK_DEV void fft1d(args const &a) {
 // writes through the digit reversal ("sorted") so that pass B sees natural order -- every thread
 // holds its sub-FFTs in registers across one extra barrier instead of a second tile buffer.
 // ------------------------------------------------------------------------------------------
-enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2 };
+enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2, T_DSMEM = 3 };
+
+// Thread-block cluster primitives (sm_90+): the barrier over all CTAs of the cluster and a load from
+// another CTA's shared memory (distributed shared memory) by shared-window offset.
+#ifdef BBFFT_EMU
+BBK_DEV void cluster_sync() { ::bbfft_emu::fail(); } // clusters are exercised on the GPU tier only
+template <class SP> BBK_DEV auto ld_cluster(SP sm, int idx, unsigned) { return sm[idx]; }
+#else
+BBK_DEV void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+BBK_DEV cx<float> ld_cluster(const cx<float> *sm, int idx, unsigned rank) {
+    const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(sm + idx));
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    cx<float> v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
+    return v;
+}
+BBK_DEV cx<double> ld_cluster(const cx<double> *sm, int idx, unsigned rank) {
+    const unsigned local = static_cast<unsigned>(__cvta_generic_to_shared(sm + idx));
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    cx<double> v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(remote) : "memory");
+    return v;
+}
+#endif
 
 // Asynchronous global -> shared copies (cp.async, one element per instruction: the padded tile
 // layout puts every element at its own 8- / 16-byte aligned slot).  The copy engine of the SM moves
@@ -1432,7 +1461,8 @@ struct no_hook {
 };
 
 template <class C, class P, int S, int SRC, int DST, class HOOK = no_hook>
-BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK after_loads = HOOK{}) {
+BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK after_loads = HOOK{},
+                        unsigned rank = 0) {
     using T = typename C::real_t;
     constexpr int R = P::radix(S);
     constexpr int NS = pass_ns<P>(S);
@@ -1452,12 +1482,22 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
         if (TOTAL % C::THREADS == 0 || id < TOTAL) {
             const int lo = id % P::S, r = id / P::S;
             const int u = r % NSUB, hi = r / NSUB;
-            const int base = lo + P::S * ((u / NS1) * NS + u % NS1) + P::S * P::N * hi;
+            const int pos0 = (u / NS1) * NS + u % NS1; // position along the axis of input j = 0
+            const int base = lo + P::S * pos0 + P::S * P::N * hi;
             static_for<0, R>([&](auto jj) {
                 constexpr int j = decltype(jj)::value;
-                const int lin = base + P::S * NS1 * j;
+                [[maybe_unused]] const int lin = base + P::S * NS1 * j;
                 if constexpr (SRC == T_GLOBAL) {
-                    v[i][j] = C::ld(a.in, gbase + u64(lin));
+                    // (P::GS: element stride of the axis in global memory; differs from the shared-memory
+                    // stride P::S only for the cluster kernel's column pass)
+                    v[i][j] = C::ld(a.in, gbase + u64(lo + P::GS * (pos0 + NS1 * j) + P::GS * P::N * hi));
+                } else if constexpr (SRC == T_DSMEM) {
+                    // cluster kernel, first stage of the column pass: row n2 of the tile lives in the shared
+                    // memory of CTA n2 / N2L in the row-pass layout  m + M (n1 + N1 n2l);  this CTA owns the
+                    // columns n1 = rank * N1L + n1l, and lo = m + M n1l
+                    const int n2 = pos0 + NS1 * j;
+                    const int owner = n2 / C::N2L, n2l = n2 % C::N2L;
+                    v[i][j] = ld_cluster(sm, tile_phys<C>(lo + int(rank) * P::S + C::ROWLEN * n2l), unsigned(owner));
                 } else {
                     v[i][j] = sm[tile_phys<C>(lin)];
                 }
@@ -1466,6 +1506,9 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
     });
     if constexpr (DST == T_SMEM_SORTED && SRC != T_GLOBAL) {
         BBK_SYNC(); // every read of the stage happens before its out-of-place writes
+    }
+    if constexpr (SRC == T_DSMEM) {
+        cluster_sync(); // every CTA of the cluster has gathered its columns: the row-pass layout is dead everywhere
     }
     if constexpr (HOOK::active) {
         static_assert(SRC == T_SMEM && DST == T_GLOBAL, "the hook belongs to the stage that empties shared memory");
@@ -1493,14 +1536,14 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
                     sm[tile_phys<C>(base + P::S * NS1 * q)] = v[i][q];
                 });
             } else {
-                const int base = lo + P::S * bin_of_sub<P>(u) + P::S * P::N * hi;
+                const int bin0 = bin_of_sub<P>(u);
+                [[maybe_unused]] const int base = lo + P::S * bin0 + P::S * P::N * hi;
                 static_for<0, R>([&](auto qq) {
                     constexpr int q = decltype(qq)::value;
-                    const int lin = base + P::S * (P::N / R) * q;
                     if constexpr (DST == T_GLOBAL) {
-                        C::st(a.out, gbase + u64(lin), v[i][q]);
+                        C::st(a.out, gbase + u64(lo + P::GS * (bin0 + (P::N / R) * q) + P::GS * P::N * hi), v[i][q]);
                     } else {
-                        sm[tile_phys<C>(lin)] = v[i][q];
+                        sm[tile_phys<C>(base + P::S * (P::N / R) * q)] = v[i][q];
                     }
                 });
             }
@@ -1509,7 +1552,8 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
 }
 
 template <class C, class P, int S, int SRC0, int DSTL, class HOOK = no_hook>
-BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK last_hook = HOOK{}) {
+BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 gbase, int tid, HOOK last_hook = HOOK{},
+                       unsigned rank = 0) {
     if constexpr (S < P::L) {
         constexpr int SRC = (S == 0) ? SRC0 : T_SMEM;
         constexpr int DST = (S == P::L - 1) ? DSTL : T_SMEM;
@@ -1517,11 +1561,11 @@ BBK_DEV void tile_pass(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 g
             BBK_SYNC();
         }
         if constexpr (S == P::L - 1 && HOOK::active) {
-            tile_stage<C, P, S, SRC, DST, HOOK>(a, sm, gbase, tid, last_hook);
+            tile_stage<C, P, S, SRC, DST, HOOK>(a, sm, gbase, tid, last_hook, rank);
         } else {
-            tile_stage<C, P, S, SRC, DST>(a, sm, gbase, tid);
+            tile_stage<C, P, S, SRC, DST>(a, sm, gbase, tid, no_hook{}, rank);
         }
-        tile_pass<C, P, S + 1, SRC0, DSTL, HOOK>(a, sm, gbase, tid, last_hook);
+        tile_pass<C, P, S + 1, SRC0, DSTL, HOOK>(a, sm, gbase, tid, last_hook, rank);
     }
 }
 
@@ -1583,9 +1627,36 @@ template <class C> BBK_DEV void fft2d_tile_persistent(args const &a) {
     }
 }
 
+// Cluster variant (C::CL > 1 CTAs per tile, thread-block cluster of CL, distributed shared memory).
+// A 128 x 128 fp32 tile is 128 KiB: one CTA per SM, and a stage-synchronised CTA that is alone on its SM
+// overlaps nothing with its own load latency (round 1: 0.65 of the HBM peak, against 0.96 for the 32 KiB
+// 64 x 64 tiles that run four to an SM).  Here CTA `rank` of the cluster holds N2 / CL ROWS of the tile
+// (32 KiB for CL = 4), so CTAs of several tiles share an SM again.  Row pass: local.  Column pass: CTA
+// `rank` takes the columns n1 in [rank N1/CL, (rank+1) N1/CL); the first stage pulls its inputs straight
+// out of the owners' shared memory (ld.shared::cluster), one cluster barrier later every CTA reuses its
+// own shared memory for the rest of the column pass, and the last stage stores N1/CL-element runs of
+// every row to global memory.  HBM traffic stays one read and one write of the tile.
+template <class C> BBK_DEV void fft2d_tile_cluster(args const &a) {
+    using T = typename C::real_t;
+    using PA = typename C::PA;
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const u64 tile = BBK_BID() / u64(C::CL);
+    const unsigned rank = unsigned(BBK_BID() % u64(C::CL));
+    const u64 gtile = tile * u64(C::TILE_STRIDE);
+    // rows n2 in [rank N2L, (rank+1) N2L): a contiguous slab of the tile
+    tile_pass<C, PA, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, gtile + u64(rank) * u64(PA::S * PA::N * PA::O), tid);
+    cluster_sync(); // every CTA's rows are transformed and visible to the cluster
+    // columns: lo = m + M n1l runs over this CTA's PB::S = M N1L fastest positions; in global memory they
+    // start at rank * PB::S inside every row of the tile
+    tile_pass<C, typename C::PB, 0, T_DSMEM, T_GLOBAL>(a, sm, gtile + u64(rank) * u64(C::PB::S), tid, no_hook{}, rank);
+}
+
 template <class C> BBK_DEV void fft2d_tile(args const &a) {
     pdl_prologue();
-    if constexpr (C::PERSIST) {
+    if constexpr (C::CL > 1) {
+        fft2d_tile_cluster<C>(a);
+    } else if constexpr (C::PERSIST) {
         fft2d_tile_persistent<C>(a);
     } else {
         const u64 tile = BBK_BID();

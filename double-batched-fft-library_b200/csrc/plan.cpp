@@ -162,19 +162,89 @@ shared_handle<module_handle_t> builtin_module(std::string const &kernel_name, in
     return {};
 }
 
-// JIT policy: no spills under a register cap.  The planner caps registers with __maxnreg__ so that
-// the planned number of CTAs is resident; when NVRTC's ptxas can only meet the cap by spilling, the
-// kernel is rebuilt without the cap (it then runs with fewer resident CTAs, never with local-memory
-// traffic).  Besides being slow, the spill path of ptxas 12.9 miscompiled one such kernel in round 1
-// (fp64 c2r M=32 N=424 r4x53: an output index rematerialised from a dead register, see
-// profiles/r02b_ptxas_miscompile.md), so capped-and-spilling JIT kernels are not trusted.
-static shared_handle<module_handle_t> jit_module(api const &a, std::string const &source, std::string const &name,
-                                                 std::size_t smem_bytes) {
-    auto mod = a.build_module(source);
+// JIT policy: a capped kernel that spills must prove itself.  The planner caps registers with
+// __maxnreg__ so that the planned number of CTAs is resident; when NVRTC's ptxas can only meet the cap
+// by spilling, the result comes out of the spill / rematerialisation path of ptxas -- the path that
+// miscompiled one kernel in round 1 (fp64 c2r M=32 N=424 r4x53: a store address built from a dead
+// register, profiles/r02b_ptxas_miscompile.md).  Such a kernel is kept only if it reproduces, bit for
+// bit, the output of the same source built WITHOUT the cap on a probe problem (every multiply is an
+// explicit-rounding intrinsic, so two correct builds are bit-identical: the property the callback
+// tests rely on).  Otherwise -- or when the probe cannot be run (user callbacks address memory the
+// plan knows nothing about) -- the uncapped build is used: fewer resident CTAs, never a wrong
+// result.  BBFFT_CUDA_KEEP_REGCAP=1 skips all of this (tuning runs).
+struct jit_result {
+    shared_handle<module_handle_t> mod;     // the build to use
+    shared_handle<module_handle_t> relaxed; // the uncapped build when the capped one spills and is still to be probed
+};
+
+static jit_result jit_module(api const &a, std::string const &source, std::string const &name,
+                             std::size_t smem_bytes, bool can_probe) {
+    jit_result r;
+    r.mod = a.build_module(source);
     char const *keep = std::getenv("BBFFT_CUDA_KEEP_REGCAP");
-    if (keep && *keep == '1') return mod;
-    if (a.kernel_local_bytes(a.create_kernel(mod.get(), name, smem_bytes)) == 0) return mod;
-    return a.build_module(source, {"-DBBK_NO_REGCAP"});
+    if (keep && *keep == '1') return r;
+    if (a.kernel_local_bytes(a.create_kernel(r.mod.get(), name, smem_bytes)) == 0) return r;
+    auto relaxed = a.build_module(source, {"-DBBK_NO_REGCAP"});
+    if (can_probe) {
+        r.relaxed = relaxed;
+    } else {
+        r.mod = relaxed;
+    }
+    return r;
+}
+
+// Run `capped` and `relaxed` (same kernel arguments except the output) on a probe tensor and compare
+// the outputs byte for byte.
+static bool probe_identical(api const &a, cudaKernel_t capped, cudaKernel_t relaxed, std::uint64_t grid, int threads,
+                            std::size_t smem_bytes, kernel_args args, std::size_t in_bytes, std::size_t out_bytes, int fp) {
+    // input: reproducible values in (-1, 1) of the tensor's precision (any bit pattern would do for
+    // bit-identity, finite values keep NaN != NaN out of the comparison)
+    std::vector<unsigned char> host_in(in_bytes);
+    {
+        std::uint32_t s = 2463534242u;
+        auto next = [&] {
+            s ^= s << 13;
+            s ^= s >> 17;
+            s ^= s << 5;
+            return double(s >> 8) / double(1u << 23) - 1.0;
+        };
+        if (fp == 4) {
+            auto *f = reinterpret_cast<float *>(host_in.data());
+            for (std::size_t i = 0; i < in_bytes / 4; ++i) f[i] = float(next());
+        } else {
+            auto *f = reinterpret_cast<double *>(host_in.data());
+            for (std::size_t i = 0; i < in_bytes / 8; ++i) f[i] = next();
+        }
+    }
+    void *din = a.create_device_buffer(in_bytes);
+    void *d1 = a.create_device_buffer(out_bytes);
+    void *d2 = a.create_device_buffer(out_bytes);
+    bool same = false;
+    try {
+        cudaStream_t st = a.stream();
+        BBFFT_CUDA_CHECK(cudaMemcpyAsync(din, host_in.data(), in_bytes, cudaMemcpyHostToDevice, st));
+        BBFFT_CUDA_CHECK(cudaMemsetAsync(d1, 0x5a, out_bytes, st));
+        BBFFT_CUDA_CHECK(cudaMemsetAsync(d2, 0x5a, out_bytes, st));
+        args.in = din;
+        args.out = d1;
+        a.launch_kernel(capped, grid, threads, smem_bytes, args, st);
+        args.out = d2;
+        a.launch_kernel(relaxed, grid, threads, smem_bytes, args, st);
+        std::vector<unsigned char> h1(out_bytes), h2(out_bytes);
+        BBFFT_CUDA_CHECK(cudaMemcpyAsync(h1.data(), d1, out_bytes, cudaMemcpyDeviceToHost, st));
+        BBFFT_CUDA_CHECK(cudaMemcpyAsync(h2.data(), d2, out_bytes, cudaMemcpyDeviceToHost, st));
+        BBFFT_CUDA_CHECK(cudaStreamSynchronize(st));
+        same = h1 == h2;
+    } catch (...) {
+        a.release_buffer(din);
+        a.release_buffer(d1);
+        a.release_buffer(d2);
+        throw;
+    }
+    a.release_buffer(din);
+    a.release_buffer(d1);
+    a.release_buffer(d2);
+    return same;
 }
 
 // Launches go to the plan's device whatever device is current in the calling thread (the kernel
@@ -244,12 +314,36 @@ fft1d_plan::fft1d_plan(configuration const &cfg, api a, jit_cache *cache, std::s
     jit_cache_key key{kp_.identifier, api_.device_id()};
     if (cache) module_ = cache->get(key);
     if (!module_ && prob.cb_source.empty()) module_ = builtin_module(kp_.identifier, api_.device());
+    jit_result jit;
     if (!module_) {
-        module_ = jit_module(api_, kp_.source, kp_.identifier, kp_.p.smem_bytes);
-        if (cache) cache->store(key, module_);
+        jit = jit_module(api_, kp_.source, kp_.identifier, kp_.p.smem_bytes, prob.cb_source.empty() && prob.K > 0);
+        module_ = jit.mod;
     }
     kernel_ = api_.create_kernel(module_.get(), kp_.identifier, kp_.p.smem_bytes);
     twiddle_ = api_.create_twiddle_table(kp_.twiddle, kp_.p.fp);
+    if (jit.relaxed) {
+        // the capped build spills: probe it against the uncapped build on a few CTAs' worth of slices
+        cudaKernel_t relaxed = api_.create_kernel(jit.relaxed.get(), kp_.identifier, kp_.p.smem_bytes);
+        const std::uint64_t kt = std::min<std::uint64_t>(prob.K, 3 * kp_.p.k_per_cta() + 1);
+        kernel_args pa;
+        pa.tw = twiddle_;
+        pa.K = kt;
+        pa.M = kp_.p.M;
+        pa.is1 = kp_.p.is1;
+        pa.is2 = kp_.p.is2;
+        pa.os1 = kp_.p.os1;
+        pa.os2 = kp_.p.os2;
+        pa.pf = 0;
+        pa.in = nullptr;
+        pa.out = nullptr;
+        const std::size_t ib = in_required_ - (prob.K - kt) * in_slice_bytes_;
+        const std::size_t ob = out_required_ - (prob.K - kt) * out_slice_bytes_;
+        if (!probe_identical(api_, kernel_, relaxed, kp_.p.grid(kt), kp_.p.threads, kp_.p.smem_bytes, pa, ib, ob, kp_.p.fp)) {
+            module_ = jit.relaxed;
+            kernel_ = relaxed;
+        }
+    }
+    if (jit.mod && cache) cache->store(key, module_); // JIT-built here (not taken from a cache): publish the build in use
     prefetch_ = prefetch_distance(api_, kernel_, kp_.p.threads, kp_.p.smem_bytes, kp_.p.min_blocks,
                                   kp_.p.klanes ? 1 : (kp_.p.M + kp_.p.ML - 1) / kp_.p.ML);
 }
@@ -363,7 +457,8 @@ fft2d_plan::fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::str
     if (cache) module_ = cache->get(key);
     if (!module_) module_ = builtin_module(tp_.identifier, api_.device());
     if (!module_) {
-        module_ = jit_module(api_, tp_.source, tp_.identifier, tp_.p.smem_bytes);
+        // (tile kernels that spill under their cap run uncapped: no probe)
+        module_ = jit_module(api_, tp_.source, tp_.identifier, tp_.p.smem_bytes, false).mod;
         if (cache) cache->store(key, module_);
     }
     kernel_ = api_.create_kernel(module_.get(), tp_.identifier, tp_.p.smem_bytes);
@@ -397,12 +492,12 @@ void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
         api_.launch_kernel(kernel_, std::min<std::uint64_t>(count, resident_ctas_), tp_.p.threads, tp_.p.smem_bytes, a, stream);
         return;
     }
-    api_.launch_kernel(kernel_, count, tp_.p.threads, tp_.p.smem_bytes, a, stream);
+    api_.launch_kernel(kernel_, count * std::uint64_t(tp_.p.cluster), tp_.p.threads, tp_.p.smem_bytes, a, stream);
 }
 
 // Steps of a 2d/3d plan.  c2c transforms in the default layout whose M x N1 x N2 tile fits into
 // shared memory run modes 1 and 2 fused (BBFFT_CUDA_ND_FUSE=0 turns this off: "multi-pass").
-std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev) {
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain) {
     std::vector<nd_step> steps;
     const std::uint64_t K = cfg.shape[cfg.dim + 1];
     std::vector<configuration> passes;
@@ -418,7 +513,7 @@ std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &
         t.N2 = cfg.shape[2];
         t.K = (cfg.dim == 3 ? cfg.shape[3] : 1) * K;
         t.tile_stride = t.M * t.N1 * t.N2;
-        fuse = tile_fusable(t, dev);
+        fuse = tile_fusable(t, dev, for_chain ? 1 : tile_cluster_limit());
     }
     std::size_t first = 0;
     if (fuse) {
@@ -476,7 +571,7 @@ bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
     if (cache) chain_module_ = cache->get(key);
     if (!chain_module_) chain_module_ = builtin_module(chain_.identifier, api_.device());
     if (!chain_module_) {
-        chain_module_ = jit_module(api_, chain_.source, chain_.identifier, chain_.smem_bytes);
+        chain_module_ = jit_module(api_, chain_.source, chain_.identifier, chain_.smem_bytes, false).mod;
         if (cache) cache->store(key, chain_module_);
     }
     chain_kernel_ = api_.create_kernel(chain_module_.get(), chain_.identifier, chain_.smem_bytes);
@@ -506,8 +601,11 @@ bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
 
 nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::move(a)), dim_(cfg.dim) {
     K_ = cfg.shape[dim_ + 1];
-    auto steps = nd_decompose(cfg, api_.props());
+    char const *chain_env = std::getenv("BBFFT_CUDA_ND_CHAIN");
+    const bool want_chain = chain_env && *chain_env == '1';
+    auto steps = nd_decompose(cfg, api_.props(), want_chain);
     chained_ = try_chain(steps, cache);
+    if (want_chain && !chained_) steps = nd_decompose(cfg, api_.props(), false);
     for (auto const &s : steps) {
         if (chained_) {
             mult_.push_back(s.mult);
@@ -655,7 +753,7 @@ std::vector<std::string> generate_fft_kernels(std::ostream &os, std::vector<conf
             {
                 // the persistent chain kernel nd_plan launches when the steps can share a CTA shape
                 std::vector<cuda::chain_step_problem> probs;
-                for (auto const &st : steps) {
+                for (auto const &st : cuda::nd_decompose(cfg, dev, true)) {
                     cuda::chain_step_problem q;
                     q.tile = st.fused;
                     q.mult = st.mult;

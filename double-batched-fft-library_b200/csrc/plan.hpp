@@ -135,7 +135,8 @@ struct nd_step {
     configuration pass;
     std::uint64_t mult = 1;
 };
-std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev);
+// (for_chain: steps of one persistent chain kernel -- the fused tile must fit a single CTA)
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain = false);
 
 class nd_plan : public plan_base {
   public:

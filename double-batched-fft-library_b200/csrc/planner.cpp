@@ -1134,12 +1134,27 @@ std::size_t tile_smem_bytes(std::uint64_t tile, int padk, int fp) {
 
 } // namespace
 
-bool tile_fusable(problem_2d const &prob, device_props const &dev) {
+int tile_cluster_limit() {
+    if (char const *e = std::getenv("BBFFT_CUDA_TILE_CLUSTER")) {
+        int want = std::atoi(e);
+        if (want >= 1 && want <= 8 && (want & (want - 1)) == 0) return want;
+    }
+    return 1;
+}
+
+bool tile_fusable(problem_2d const &prob, device_props const &dev, int max_cluster) {
     if (prob.N1 < 2 || prob.N2 < 2) return false;
     const std::uint64_t tile = prob.M * prob.N1 * prob.N2;
     if (tile < 1024 || tile > (1u << 20)) return false;
-    // padding candidates that would not fit are skipped by the layout search
-    if (tile_smem_bytes(tile, 0, prob.fp) > std::min<std::size_t>(dev.max_smem_per_block, 200 * 1024)) return false;
+    // padding candidates that would not fit are skipped by the layout search; a tile that does not fit one
+    // CTA is split over a thread-block cluster of up to 8 (plan_kernel_2d)
+    std::uint64_t local = tile;
+    for (int cl = 1; cl < max_cluster && tile_smem_bytes(local, 0, prob.fp) > std::min<std::size_t>(dev.max_smem_per_block, 200 * 1024) &&
+                     prob.N1 % (2 * cl) == 0 && prob.N2 % (2 * cl) == 0;
+         cl *= 2) {
+        local = tile / (2 * cl);
+    }
+    if (tile_smem_bytes(local, 0, prob.fp) > std::min<std::size_t>(dev.max_smem_per_block, 200 * 1024)) return false;
     int big = std::max(max_prime(int(prob.N1)), max_prime(int(prob.N2)));
     return big <= 31;
 }
@@ -1170,8 +1185,37 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         q.L = int(r.size());
         for (int s = 0; s < 4; ++s) q.radix[s] = s < q.L ? r[s] : 1;
     };
-    fill(p.a, ra, int(prob.N1), int(prob.M), int(prob.N2));
-    fill(p.b, rb, int(prob.N2), int(prob.M * prob.N1), 1);
+    // CTAs per tile (bbk::fft2d_tile_cluster: the tile split over a thread-block cluster, rows N2 / CL per CTA
+    // in the row pass, columns N1 / CL in the column pass, gathered through distributed shared memory).
+    // A switch, OFF by default (CL=<n> / BBFFT_CUDA_TILE_CLUSTER=<n>): it was built to put several tiles' CTAs
+    // on one SM for the 128 KiB tiles that run one CTA per SM, and measured on the B200 it loses
+    // (profiles/r02f_cluster.txt: 2d fp32 128x128 at 1 GiB 524 us with one CTA per tile, 545 us with CL=4,
+    // 750 / 785 us with CL=2 / 8; 3d fp64 64^3 191 -> 200 us with CL=2) -- the remote gather and the two
+    // cluster barriers cost more than the extra resident CTAs buy.  With the switch on, tiles of up to
+    // 8 x 200 KiB are fused instead of falling back to one launch per mode.
+    {
+        int cl = 1;
+        const bool chained_req = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
+        auto ok = [&](int c) {
+            return prob.N1 % c == 0 && prob.N2 % c == 0 && (tile / c) * 2 * std::uint64_t(prob.fp) >= 16 * 1024 &&
+                   (prob.M * prob.N1 / c) * 2 * std::uint64_t(prob.fp) >= 128; // >= 128-byte runs in the final store
+        };
+        const int limit = chained_req ? 1 : tile_cluster_limit();
+        // the smallest cluster that brings the CTA's share to 32 KiB (or makes the tile fit at all)
+        while (cl < limit && (tile / cl) * 2 * std::uint64_t(prob.fp) > 32 * 1024 && ok(cl * 2)) cl *= 2;
+        if (tune.count("CL")) {
+            int want = std::atoi(tune["CL"].c_str());
+            if (want < 1 || want > 8 || (want & (want - 1)) != 0 || prob.N1 % want != 0 || prob.N2 % want != 0 || (chained_req && want != 1)) {
+                throw bad_configuration("bbfft-cuda planner: bad tile cluster size");
+            }
+            cl = want;
+        }
+        p.cluster = cl;
+    }
+    const std::uint64_t local_tile = tile / std::uint64_t(p.cluster);
+    // row pass over the CTA's N2 / CL rows; column pass over its N1 / CL columns (S = fastest run M * N1 / CL)
+    fill(p.a, ra, int(prob.N1), int(prob.M), int(prob.N2) / p.cluster);
+    fill(p.b, rb, int(prob.N2), int(prob.M * prob.N1) / p.cluster, 1);
 
     // threads: ~16 (fp32) / ~8-16 (fp64) complex elements per thread
     if (tune.count("TH")) {
@@ -1179,9 +1223,9 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     } else {
         // fp32 64 x 64 tiles: 128 threads with 32 elements each (four resident CTAs) measured 6273 GB/s
         // against 5603 GB/s for 256 threads (profiles/r01h_tile_tune.json)
-        const std::uint64_t ept = (p.fp == 4 && tile == 4096) ? 32 : 16;
+        const std::uint64_t ept = (p.fp == 4 && local_tile == 4096) ? 32 : 16;
         int th = 64;
-        while (th < dev.max_threads_per_block && std::uint64_t(th) * ept < tile) th *= 2;
+        while (th < dev.max_threads_per_block && std::uint64_t(th) * ept < local_tile) th *= 2;
         p.threads = th;
     }
     if (p.threads < 32 || p.threads > dev.max_threads_per_block || p.threads % 32) {
@@ -1192,7 +1236,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         long best = -1;
         int best_padk = 0;
         for (int padk : {0, 64, 32, 16, 8}) {
-            if (tile_smem_bytes(tile, padk, p.fp) > dev.max_smem_per_block) continue;
+            if (tile_smem_bytes(local_tile, padk, p.fp) > dev.max_smem_per_block) continue;
             long sc = tile_layout_score(p, padk) * 64 + (padk ? 64 / padk : 0);
             if (best < 0 || sc < best) {
                 best = sc;
@@ -1202,7 +1246,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         p.PADK = best_padk;
     }
     if (tune.count("PADK")) p.PADK = std::atoi(tune["PADK"].c_str());
-    p.smem_bytes = tile_smem_bytes(tile, p.PADK, p.fp);
+    p.smem_bytes = tile_smem_bytes(local_tile, p.PADK, p.fp);
     if (p.smem_bytes > dev.max_smem_per_block) {
         throw bad_configuration("bbfft-cuda planner: tile does not fit into shared memory");
     }
@@ -1219,10 +1263,16 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
     p.max_regs = reg_cap(p.threads, p.min_blocks);
     p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
-    // persistent grid + asynchronous load of the next tile (PS=0 / BBFFT_CUDA_TILE_ASYNC=0: one tile per CTA)
-    p.persistent = !p.chained;
-    if (char const *e = std::getenv("BBFFT_CUDA_TILE_ASYNC")) p.persistent = p.persistent && *e != '0';
+    // Persistent grid + asynchronous load of the next tile (bbk::fft2d_tile_persistent): a switch
+    // (PS=1 / BBFFT_CUDA_TILE_ASYNC=1), off by default.  Measured on the B200 (profiles/r02e_tile_pdl.txt)
+    // it loses a little -- 2d fp32 128x128 at 1 GiB: 517 us against 499 us; 3d fp64 64^3: 204 against
+    // 188 us -- because the one-tile-per-CTA kernel already overlaps the store drain of tile i with the
+    // loads of the CTA that replaces it, so only the last stage's arithmetic is left to hide, and the
+    // extra trip through shared memory plus the barrier cost more than that.
+    p.persistent = false;
+    if (char const *e = std::getenv("BBFFT_CUDA_TILE_ASYNC")) p.persistent = !p.chained && *e == '1';
     if (tune.count("PS")) p.persistent = !p.chained && std::atoi(tune["PS"].c_str()) != 0;
+    if (p.cluster > 1) p.persistent = false;
 
     // identifier
     {
@@ -1235,6 +1285,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         os << "_th" << p.threads << "_mb" << p.min_blocks << "_pk" << p.PADK << "_ts" << p.tile_stride;
         if (p.chained) os << "_ch";
         if (p.persistent) os << "_ps";
+        if (p.cluster > 1) os << "_cl" << p.cluster;
         plan.identifier = os.str();
     }
     // twiddles: pass A stages, then pass B stages (same construction as the 1d table)
@@ -1275,9 +1326,9 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         for (int s = 0; s < p.a.L; ++s) rs.insert(p.a.radix[s]);
         for (int s = 0; s < p.b.L; ++s) rs.insert(p.b.radix[s]);
         for (int r : rs) emit_w_table(os, r);
-        auto emit_pass = [&](char const *name, tile_pass_params const &q, std::vector<int> const &off) {
+        auto emit_pass = [&](char const *name, tile_pass_params const &q, std::vector<int> const &off, long gs) {
             os << "struct " << name << " {\n    static constexpr int N = " << q.N << ", S = " << q.S << ", O = " << q.O
-               << ", L = " << q.L << ";\n";
+               << ", L = " << q.L << ", GS = " << gs << ";\n";
             os << "    static BBK_CE int radix(int s) {\n        constexpr int r[4] = {" << q.radix[0] << ", "
                << q.radix[1] << ", " << q.radix[2] << ", " << q.radix[3] << "};\n        return r[s];\n    }\n";
             os << "    static BBK_CE int tw_off(int s) {\n        constexpr int r[4] = {" << off[0] << ", " << off[1]
@@ -1289,10 +1340,11 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
             }
             os << "    template <int S_> using WR = typename WRsel<S_>::type;\n};\n";
         };
-        emit_pass("PassA", p.a, off_a);
-        emit_pass("PassB", p.b, off_b);
+        emit_pass("PassA", p.a, off_a, long(p.a.S));
+        emit_pass("PassB", p.b, off_b, long(prob.M * prob.N1)); // rows of the whole tile in global memory
         os << "struct C {\n    using real_t = " << real << ";\n    using PA = PassA;\n    using PB = PassB;\n";
         os << "    static constexpr int DIR = " << p.dir << ", THREADS = " << p.threads << ", PADK = " << p.PADK
+           << ", CL = " << p.cluster << ", N2L = " << (prob.N2 / std::uint64_t(p.cluster)) << ", ROWLEN = " << (prob.M * prob.N1)
            << ";\n    static constexpr bool PERSIST = " << (p.persistent ? "true" : "false")
            << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull;\n";
         if (p.chained) {
@@ -1306,8 +1358,9 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
               "        reinterpret_cast<bbk::cx<real_t> *>(out)[off] = v;\n    }\n";
         os << "};\n} // namespace stub_" << plan.identifier << "\n";
         if (!p.chained) {
-            os << "extern \"C\" BBK_GLOBAL void BBK_KERNEL(" << p.threads << ", " << p.max_regs << ") " << plan.identifier
-               << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
+            os << "extern \"C\" BBK_GLOBAL void BBK_KERNEL(" << p.threads << ", " << p.max_regs << ") ";
+            if (p.cluster > 1) os << "BBK_CLUSTER(" << p.cluster << ") ";
+            os << plan.identifier << "(bbk::args a) {\n    bbk::fft2d_tile<stub_" << plan.identifier << "::C>(a);\n}\n";
         }
         plan.source = os.str();
     }

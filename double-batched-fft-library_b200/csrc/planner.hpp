@@ -102,6 +102,7 @@ struct tile_params {
     tile_pass_params a, b; // axis n1, axis n2
     int threads = 256, PADK = 0, min_blocks = 1, max_regs = 255;
     bool persistent = false; // persistent grid with the asynchronous tile pipeline (bbk::fft2d_tile_persistent)
+    int cluster = 1;         // CTAs per tile (thread-block cluster, bbk::fft2d_tile_cluster); 1 = one CTA owns the tile
     std::size_t smem_bytes = 0;
     bool chained = false; // see kernel_params::chained
 };
@@ -114,7 +115,10 @@ struct tile_plan {
 
 // True when the M x N1 x N2 tile (plus padding) fits the shared memory of one CTA and is large
 // enough to be worth a CTA of its own.
-bool tile_fusable(problem_2d const &prob, device_props const &dev);
+// largest thread-block cluster a tile may be split over (BBFFT_CUDA_TILE_CLUSTER, default 1 = off)
+int tile_cluster_limit();
+// (max_cluster = 1: the tile must fit one CTA)
+bool tile_fusable(problem_2d const &prob, device_props const &dev, int max_cluster = 1);
 // Tuning overrides: RA=8x16, RB=16x8, TH=<threads>, PADK, MB.
 tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev,
                          std::string const &tune = std::string());

@@ -408,14 +408,18 @@ cudaKernel_t api::create_kernel(module_handle_t mod, std::string const &name, st
     return k;
 }
 
-// BBFFT_CUDA_PDL=1: launches carry the programmatic-stream-serialization attribute (see
-// bbk::pdl_prologue in the device header)
-static bool pdl_enabled() {
-    static const bool on = [] {
+// Programmatic dependent launch (see bbk::pdl_prologue in the device header): launches of SMALL grids
+// -- at most two waves of CTAs, where the launch latency is a visible share of the kernel (measured on
+// BASELINE config 1: 6.15 -> 4.45 us per back-to-back execute, profiles/r02e_tile_pdl.txt) -- carry
+// the programmatic-stream-serialization attribute.  Large grids gain nothing, and inside a stream
+// capture the programmatic edge costs time (3.77 -> 4.41 us per graph node), so captured launches
+// and large grids are launched plainly.  BBFFT_CUDA_PDL=0 switches it off, =2 forces it everywhere.
+static int pdl_mode() {
+    static const int mode = [] {
         char const *e = std::getenv("BBFFT_CUDA_PDL");
-        return e && *e == '1';
+        return e ? std::atoi(e) : 1;
     }();
-    return on;
+    return mode;
 }
 
 void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::size_t smem_bytes,
@@ -426,7 +430,12 @@ void api::launch_kernel(cudaKernel_t k, std::uint64_t grid, int threads, std::si
     }
     kernel_args a = args;
     void *params[] = {&a};
-    if (pdl_enabled()) {
+    bool pdl = pdl_mode() == 2;
+    if (pdl_mode() == 1 && std::uint64_t(threads) * grid <= 2ull * 2048ull * std::uint64_t(props_.sm_count)) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        pdl = cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    }
+    if (pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(unsigned(grid));
         cfg.blockDim = dim3(unsigned(threads));

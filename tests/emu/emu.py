@@ -57,6 +57,10 @@ def _compile(desc):
 
 def run(cfg, inp, out=None, tune=""):
     """Execute the planned kernel for a 1d (or fused 2d) `cfg` on numpy buffers (out=None -> in place)."""
+    if cfg.dim == 2 and "CL=" not in tune:
+        # thread-block clusters (tiles split over several CTAs, distributed shared memory) are exercised on
+        # the GPU tier only: the emulator runs one CTA at a time
+        tune = (tune + "," if tune else "") + "CL=1"
     desc = pkg.describe(cfg, tune)
     lib = _compile(desc)
     lib.emu_launch.argtypes = [C.POINTER(Args), C.c_ulonglong, C.c_int, C.c_ulong]

@@ -227,3 +227,37 @@ def test_c2c_large_prime_factors_vs_oracle(pkg, oracle, fp, M, N, K):
         assert rel_l2(yd.cpu().numpy(), ref) < TOL[fp], plan.kernel_names
         assert np.array_equal(yd.cpu().numpy(), xd.cpu().numpy())
         plan.close()
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("M,N,K", [(16, 1024, 9), (1, 1024, 70), (16, 2048, 5), (3, 4096, 4), (1, 8192, 6), (16, 625, 7),
+                                   (2, 1000, 11), (16, 729, 3), (1, 6561, 3), (4, 5120, 2)])
+def test_c2c_beyond_512_single_kernel(pkg, fp, M, N, K):
+    """N in (512, 8192]: still ONE kernel (three or four shared-memory stages; the planner narrows the
+    batch lanes until a CTA's rows fit).  Outside the reference benchmark's N <= 512 sweep but inside
+    what the reference accepts; round 1 covered it on the CPU emulator only."""
+    rng = np.random.default_rng(N + M)
+    x = random_complex(rng, (K, N, M), fp)
+    for d in (pkg.FORWARD, pkg.BACKWARD):
+        cfg = pkg.make_config(1, [M, N, K], fp, d, pkg.C2C, inplace=False)
+        y, names = _exec(pkg, cfg, x, np.zeros_like(x))
+        ref = np.fft.fft(x.astype(np.complex128), axis=1) if d < 0 else np.fft.ifft(x.astype(np.complex128), axis=1) * N
+        assert rel_l2(y, ref) < TOL[fp], names
+    cfg = pkg.make_config(1, [M, N, K], fp, pkg.FORWARD, pkg.C2C, inplace=True)
+    y, names = _exec(pkg, cfg, x.copy())
+    assert rel_l2(y, np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[fp], names
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("M,N,K", [(16, 1024, 6), (1, 4096, 10), (2, 1250, 8), (1, 2187, 4)])
+def test_real_beyond_512_single_kernel(pkg, fp, M, N, K):
+    rng = np.random.default_rng(N * 3 + M)
+    x = rng.uniform(-1, 1, (K, N, M)).astype(np.float32 if fp == 4 else np.float64)
+    cfg = pkg.make_config(1, [M, N, K], fp, pkg.FORWARD, pkg.R2C, inplace=False)
+    spec = np.zeros((K, N // 2 + 1, M), dtype=cdtype(fp))
+    y, names = _exec(pkg, cfg, x, spec)
+    ref = np.fft.rfft(x.astype(np.float64), axis=1)
+    assert rel_l2(y, ref) < TOL[fp], names
+    cfg = pkg.make_config(1, [M, N, K], fp, pkg.BACKWARD, pkg.C2R, inplace=False)
+    back, names = _exec(pkg, cfg, y, np.zeros_like(x))
+    assert rel_l2(back / N, x) < TOL[fp] * 4, names

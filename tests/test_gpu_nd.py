@@ -22,7 +22,9 @@ def _axes(dim):
 
 @pytest.mark.parametrize("fp", [4, 8])
 @pytest.mark.parametrize("M,Ns,K", [(1, (8, 4), 3), (3, (5, 4), 7), (2, (16, 27), 2), (1, (4, 8, 2), 3), (3, (6, 5, 4), 2),
-                                    (1, (128, 128), 4), (1, (64, 64, 64), 1), (7, (10, 3), 5)])
+                                    (1, (128, 128), 4), (1, (64, 64, 64), 1), (7, (10, 3), 5),
+                                    (1, (256, 256), 3), (4, (64, 64), 5), (2, (128, 32), 9), (1, (96, 80), 7),
+                                    (16, (16, 64), 6)])
 def test_c2c_nd(pkg, fp, M, Ns, K):
     dim = len(Ns)
     rng = np.random.default_rng(sum(Ns) + M)
@@ -234,3 +236,48 @@ def test_config4_3d_chain_full_size(pkg, monkeypatch):
     want = torch.fft.fftn(torch.view_as_complex(x).view(K, 64, 64, 64)[:2], dim=(1, 2, 3))
     got = torch.view_as_complex(outs["chain"][0]).view(K, 64, 64, 64)[:2]
     assert float((got - want).norm() / want.norm()) < TOL[8]
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("cl", [2, 4, 8])
+@pytest.mark.parametrize("M,Ns,K", [(1, (128, 128), 4), (1, (64, 64), 7), (1, (256, 256), 3), (1, (512, 128), 2), (4, (64, 64), 5),
+                                    (2, (128, 32), 9), (1, (64, 128, 4), 2), (1, (64, 64, 64), 1)])
+def test_c2c_nd_tile_split_over_a_cluster(pkg, monkeypatch, fp, cl, M, Ns, K):
+    """BBFFT_CUDA_TILE_CLUSTER=<cl>: the fused tile is split over a thread-block cluster (rows per CTA in
+    the row pass, columns in the column pass, gathered through distributed shared memory); tiles beyond
+    one CTA's shared memory become fusable.  Off by default (measured slower), kept correct: forward out
+    of place and backward in place against numpy, and bit-identical to the one-CTA-per-tile kernel."""
+    dim = len(Ns)
+    rng = np.random.default_rng(sum(Ns) + M + cl)
+    shape_np = (K,) + tuple(reversed(Ns)) + (M,)
+    x = (rng.standard_normal(shape_np) + 1j * rng.standard_normal(shape_np)).astype(cdtype(fp))
+    outs = {}
+    for mode in ("cluster", "plain"):
+        if mode == "cluster":
+            monkeypatch.setenv("BBFFT_CUDA_TILE_CLUSTER", str(cl))
+        else:
+            monkeypatch.delenv("BBFFT_CUDA_TILE_CLUSTER", raising=False)
+        res = []
+        for d, inplace in ((pkg.FORWARD, False), (pkg.BACKWARD, True)):
+            cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, d, pkg.C2C, inplace=inplace)
+            plan = pkg.Plan(cfg, stream=_stream())
+            xd = torch.from_numpy(x).cuda()
+            if inplace:
+                plan.execute(xd)
+                yd = xd
+            else:
+                yd = torch.empty_like(xd)
+                plan.execute(xd, yd)
+            torch.cuda.synchronize()
+            res.append((yd.cpu().numpy(), plan.kernel_names))
+            plan.close()
+        outs[mode] = res
+    x64 = x.astype(np.complex128)
+    refs = [np.fft.fftn(x64, axes=_axes(dim)), np.fft.ifftn(x64, axes=_axes(dim)) * np.prod(Ns)]
+    for (y, names), ref in zip(outs["cluster"], refs):
+        assert rel_l2(y, ref) < TOL[fp], names
+    tile = M * Ns[0] * Ns[1]
+    if tile * 2 * fp <= 200 * 1024 and Ns[0] % cl == 0 and Ns[1] % cl == 0 and tile * 2 * fp // cl >= 16 * 1024:
+        for (y, names), (y0, _) in zip(outs["cluster"], outs["plain"]):
+            if "_cl" in names[0]:
+                assert np.array_equal(y, y0), names
