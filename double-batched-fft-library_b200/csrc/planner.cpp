@@ -411,8 +411,10 @@ struct wisdom_special {
 };
 const wisdom_special wisdom_specials[] = {
     {0, 4, 64, 1, "R=8x8,T=8,BH=16,ST=1,MB=2"},   // BASELINE config 1 shape: 6470 GB/s (heuristic 6316)
-    {1, 4, 256, 1, "R=16x8,T=8,BH=16,MB=2"},      // config 3 r2c: 5702 GB/s (heuristic 5457)
-    {2, 4, 256, 1, "R=8x16,T=16,BH=8,LD=0,ST=0,MB=4"},// config 3 c2r: 5793 GB/s (heuristic 4588)
+    // config 3, round 2 search over 817 overrides per placement (tools/cases_c3.json, profiles/r02g_tune.txt):
+    // r2c 5979 / 5931 GB/s out of / in place (round 1: 5702), c2r 6083 / 5913 GB/s (round 1: 5793)
+    {1, 4, 256, 1, "R=16x8,T=8,BH=8,MB=6,LD=0,ST=0"},
+    {2, 4, 256, 1, "R=8x16,T=8,BH=8,MB=6,LD=0,ST=0"},
 // measured r2c / c2r entries of the M = 16 real sweep (tools/tune_gpu.py --type r2c|c2r); they
 // keep full batch lanes, so they apply to every M that is a multiple of the lane count
 #include "wisdom_real.inc"

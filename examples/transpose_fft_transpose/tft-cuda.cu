@@ -4,6 +4,10 @@
 //   (a) transpose to N x M x K, run a unit-stride batched FFT, transpose back -- three kernels and
 //       three HBM round trips, the classic way around a library without the M mode -- or
 //   (b) hand the tensor to ONE double-batched plan {M, N, K}, which walks m along the lanes.
+// And one step beyond the reference's example ("fused transpose_fft_transpose"):
+//   (c) when the RESULT is wanted with n fastest (N x M x K, e.g. for a following unit-stride stage of a
+//       pencil decomposition), the transposing store is fused into the FFT kernel through a store callback
+//       -- one kernel, one HBM round trip -- and compared with (b) followed by a separate transpose.
 // Same experiment, shapes, initial data, check and report as the reference's
 // examples/transpose_fft_transpose/tft.cpp (tests (M,N) = (16,16), (1120,32), (128,512), (70,16),
 // fp64, ~512e6 bytes per tensor), with the transposes written as a CUDA tile kernel.
@@ -21,6 +25,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <vector>
 
@@ -97,6 +102,18 @@ int run(cudaStream_t stream, size_t M, size_t N, size_t K) {
                                    bbfft::transform_type::c2c};
     auto plan_db = bbfft::make_plan(cfg_db, stream);
 
+    // (c) the same plan with a store callback that writes element (m, n, k) to n + m N + k M N:
+    // FFT + transpose in one kernel (the callback is compiled into the kernel by NVRTC)
+    char cb_src[512];
+    std::snprintf(cb_src, sizeof(cb_src),
+                  "__device__ void store_t(double2* out, size_t offset, double2 value) {\n"
+                  "    size_t m = offset %% %zuull, n = offset / %zuull %% %zuull, k = offset / %zuull;\n"
+                  "    out[n + m * %zuull + k * %zuull] = value;\n}\n",
+                  M, M, N, M * N, N, M * N);
+    bbfft::configuration cfg_fused = cfg_db;
+    cfg_fused.callbacks = {cb_src, std::strlen(cb_src), nullptr, "store_t", bbfft::kernel_language::cuda_c};
+    auto plan_fused = bbfft::make_plan(cfg_fused, stream);
+
     auto sync = [&] { CUDA_OK(cudaStreamSynchronize(stream)); };
     auto run_tft = [&] {
         transpose(stream, x, xt, int(M), int(N), K);
@@ -123,6 +140,22 @@ int run(cudaStream_t stream, size_t M, size_t N, size_t K) {
         std::printf("Error: routes differ by %g (scale %g)\n", worst, scale);
         return 1;
     }
+    // (c) against (b) + transpose: same bits (the callback only redirects the store)
+    std::vector<cplx> got_fused(size), got_bt(size);
+    init();
+    plan_fused.execute(x, X);
+    sync();
+    CUDA_OK(cudaMemcpy(got_fused.data(), X, size * sizeof(cplx), cudaMemcpyDeviceToHost));
+    plan_db.execute(x, xt);
+    transpose(stream, xt, X, int(M), int(N), K);
+    sync();
+    CUDA_OK(cudaMemcpy(got_bt.data(), X, size * sizeof(cplx), cudaMemcpyDeviceToHost));
+    if (std::memcmp(got_fused.data(), got_bt.data(), size * sizeof(cplx)) != 0) {
+        std::printf("Error: fused FFT+transpose differs from FFT followed by transpose\n");
+        return 1;
+    }
+    const double tfused = best_of(10, [&] { plan_fused.execute(x, X); sync(); });
+    const double tbt = best_of(10, [&] { plan_db.execute(x, xt); transpose(stream, xt, X, int(M), int(N), K); sync(); });
     const double t1 = best_of(10, [&] { transpose(stream, x, xt, int(M), int(N), K); sync(); });
     const double tu = best_of(10, [&] { plan_unit.execute(xt); sync(); });
     const double t2 = best_of(10, [&] { transpose(stream, xt, X, int(N), int(M), K); sync(); });
@@ -136,6 +169,8 @@ int run(cudaStream_t stream, size_t M, size_t N, size_t K) {
     std::printf("Transpose-FFT-transpose: %g s, %g GB / s\n", ttft, bw(ttft));
     std::printf("Non-unit stride FFT: %g s, %g GB / s\n", tdb, bw(tdb));
     std::printf("Speed-up: %gx\n", ttft / tdb);
+    std::printf("FFT then transpose (n-fastest result): %g s, %g GB / s\n", tbt, bw(tbt));
+    std::printf("FFT with the transposing store fused in: %g s, %g GB / s (%gx)\n", tfused, bw(tfused), tbt / tfused);
     cudaFree(X);
     cudaFree(xt);
     cudaFree(x);

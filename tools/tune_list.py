@@ -16,6 +16,8 @@ sys.path.insert(0, ROOT)
 # same planning environment as tools/warm_cache.py, so that pre-compiled candidates are cache hits
 os.environ["BBFFT_CUDA_NO_WISDOM"] = "1"
 os.environ.setdefault("BBFFT_CUDA_JIT_LINEINFO", "0")
+# candidates that spill under their cap are timed as they are (no probe, no second compile on the GPU box)
+os.environ.setdefault("BBFFT_CUDA_KEEP_REGCAP", "1")
 if os.path.isdir(os.path.join(ROOT, "kcache")):
     os.environ.setdefault("BBFFT_CUDA_KERNEL_CACHE", os.path.join(ROOT, "kcache"))
 pkg = importlib.import_module("double-batched-fft-library_b200")
@@ -45,6 +47,9 @@ def main():
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--inner", type=int, default=1, help="launches per timed sample (L2-resident configurations: 20)")
     ap.add_argument("--filler", type=int, default=1)
+    ap.add_argument("--graph", action="store_true",
+                    help="time `inner` executes replayed as one CUDA graph (launch-bound shapes: what the GPU needs per "
+                         "launch, without the Python call overhead)")
     args = ap.parse_args()
     cases = json.load(open(args.cases))
     stream = torch.cuda.current_stream().cuda_stream
@@ -68,6 +73,18 @@ def main():
         for d in ("scfo16.64*131072", "dcfo16.64*65536"):
             fillers.append(pkg.Plan(pkg.parse_descriptor(d), stream=stream))
         os.environ["BBFFT_CUDA_NO_WISDOM"] = "1"
+    graphs = {}
+    if args.graph:
+        side = torch.cuda.Stream()
+        for i, (desc, tune, inplace, alg, plan) in enumerate(built):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(args.inner):
+                    if inplace:
+                        plan.execute(x, stream=torch.cuda.current_stream().cuda_stream)
+                    else:
+                        plan.execute(x, y, stream=torch.cuda.current_stream().cuda_stream)
+            graphs[i] = g
     times = {}
     nf = 0
     import random
@@ -80,11 +97,14 @@ def main():
             desc, tune, inplace, alg, plan = built[i]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.inner):
-                if inplace:
-                    plan.execute(x)
-                else:
-                    plan.execute(x, y)
+            if args.graph:
+                graphs[i].replay()
+            else:
+                for _ in range(args.inner):
+                    if inplace:
+                        plan.execute(x)
+                    else:
+                        plan.execute(x, y)
             e1.record()
             evs.append((i, e0, e1))
             for _ in range(args.filler):
