@@ -130,7 +130,9 @@ struct host_ring {
             }
         }
         if (slot_bytes < want_slot) {
-            // first use, or a plan whose single slice exceeds the slot: drain and grow once
+            // first use, or a plan whose single slice exceeds the slot: drain all three stages and grow once
+            BBFFT_CUDA_CHECK(cudaStreamSynchronize(s_in));
+            BBFFT_CUDA_CHECK(cudaStreamSynchronize(s_k));
             BBFFT_CUDA_CHECK(cudaStreamSynchronize(s_out));
             for (int i = 0; i < SLOTS; ++i) {
                 if (in[i]) cudaFree(in[i]);

@@ -73,8 +73,11 @@ int bbfft_cuda_plan_create_tuned(bbfft_cuda_plan_t *plan, const bbfft_cuda_confi
  * in == out selects the in-place transform.  Pointers are device (or managed / pinned) memory. */
 int bbfft_cuda_plan_execute(bbfft_cuda_plan_t plan, const void *in, void *out);
 int bbfft_cuda_plan_execute_on(bbfft_cuda_plan_t plan, const void *in, void *out, void *stream);
-/* Host-buffer convenience: H2D copy of `in_bytes`, execute, D2H copy of `out_bytes`, then
- * synchronise.  Device staging buffers are owned by the plan.  host_in == host_out runs in place. */
+/* Host buffers (the reference's plans accept host USM, docs/manual/plans.rst:113-115): copy in, transform,
+ * copy out, synchronise.  k slabs travel H2D -> kernel -> D2H over a per-device ring of device slots on
+ * three streams, so both PCIe directions stay busy; layouts whose k slices are not contiguous byte ranges
+ * and 2d/3d plans are copied whole.  `in_bytes` / `out_bytes` must cover the plan's tensors
+ * (BBFFT_CUDA_BAD_CONFIGURATION otherwise).  host_in == host_out runs in place.  Thread safe. */
 int bbfft_cuda_plan_execute_host(bbfft_cuda_plan_t plan, const void *host_in, size_t in_bytes, void *host_out,
                                  size_t out_bytes);
 int bbfft_cuda_plan_destroy(bbfft_cuda_plan_t plan);

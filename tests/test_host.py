@@ -147,6 +147,8 @@ def test_persistent_kernel_cache(pkg, tmp_path, monkeypatch):
     and served from disk afterwards; a different stub or option set gets a different file."""
     import os
     d = pkg.describe(pkg.parse_descriptor("scfo16.12*7"))
+    monkeypatch.delenv("BBFFT_CUDA_KERNEL_CACHE", raising=False)  # (conftest points the suite at kcache/ when it exists)
+    monkeypatch.setenv("BBFFT_CUDA_JIT_LINEINFO", "1")
     plain = pkg.compile_to_cubin(d["source"])
     monkeypatch.setenv("BBFFT_CUDA_KERNEL_CACHE", str(tmp_path))
     first = pkg.compile_to_cubin(d["source"])
