@@ -34,17 +34,36 @@ def _install_cache_warmer(pkg):
     os.environ["BBFFT_CUDA_JIT_LINEINFO"] = "0"
     seen = set()
 
-    def warm(cfg, tune=""):
+    def warm_one(cfg, tune):
         try:
-            if cfg.dim in (1, 2):
-                d = pkg.describe(cfg, tune or "")
-                if d["identifier"] not in seen:
-                    seen.add(d["identifier"])
-                    pkg.compile_to_cubin(d["source"])
-                    # M == 1 real plans may need their unaligned twin (PAIR=0) and spilling kernels their
-                    # uncapped build: both are compiled on demand on the GPU box, they are rare
+            d = pkg.describe(cfg, tune or "")
+            if d["identifier"] not in seen:
+                seen.add(d["identifier"])
+                pkg.compile_to_cubin(d["source"])
+                # M == 1 real plans may need their unaligned twin (PAIR=0) and spilling kernels their
+                # uncapped build: both are compiled on demand on the GPU box, they are rare
         except Exception:
             pass
+
+    def warm(cfg, tune=""):
+        if cfg.dim not in (1, 2):
+            return
+        warm_one(cfg, tune)
+        if cfg.dim == 1 and not tune:
+            # the test skips at its first plan: also compile the twins its loops would reach (the other
+            # placement with default strides, the other direction of a c2c transform)
+            shape = [int(cfg.shape[i]) for i in range(3)]
+            try:
+                for inplace in (False, True):
+                    if cfg.type == pkg.C2C:
+                        for d in (pkg.FORWARD, pkg.BACKWARD):
+                            warm_one(pkg.make_config(1, shape, cfg.fp, d, pkg.C2C, inplace=inplace), "")
+                    else:
+                        warm_one(pkg.make_config(1, shape, cfg.fp, cfg.dir, cfg.type, inplace=inplace), "")
+                        other = pkg.C2R if cfg.type == pkg.R2C else pkg.R2C
+                        warm_one(pkg.make_config(1, shape, cfg.fp, -cfg.dir, other, inplace=False), "")
+            except Exception:
+                pass
 
     class WarmPlan:
         def __init__(self, cfg, stream=0, device=-1, cache=None, tune=""):
