@@ -33,10 +33,10 @@ M_BATCH = 16
 TENSOR_BYTES = 1 << 30
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch (2 GiB = 2147483648 algorithmic bytes)
 # from the ncu --set full capture of the N=64 fp32 kernel of this sweep
-NCU_TRAFFIC_PER_LAUNCH = 1073751000 + 1024024000
-NCU_TRAFFIC_SOURCE = ("profiles/r01i_ncu_full_summary.txt (c2c f32 M=16 N=64: read 1.073751 GB + write 1.024024 GB; "
-                      "f64 N=490: 1.073689 + 1.026147 GB; f32 N=343: 1.073735 + 1.022467 GB; the tail of the output "
-                      "is still dirty in L2 when the kernel ends)")
+NCU_TRAFFIC_PER_LAUNCH = 1073752000 + 1022798000
+NCU_TRAFFIC_SOURCE = ("profiles/r02j_ncu_full_summary.txt (c2c f32 M=16 N=64: read 1.073752 GB + write 1.022798 GB; "
+                      "f64 N=490: 1.073669 + 1.026042 GB; f64 N=486: 1.073745 + 1.022654 GB; f32 N=225: 1.073906 + 1.022284 GB; "
+                      "the tail of the output is still dirty in L2 when the kernel ends)")
 
 
 def sweep_sizes():

@@ -405,6 +405,23 @@ cudaKernel_t api::create_kernel(module_handle_t mod, std::string const &name, st
         BBFFT_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void *>(k),
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
     }
+    // The planner sizes occupancy by registers AND shared memory (mb CTAs x smem_bytes); without a stated
+    // preference the driver picks the L1 / shared-memory split per launch and may keep the previous kernel's
+    // split when one CTA fits, so a kernel's occupancy -- and time -- would depend on which kernel ran before
+    // it (seen as +-20 % on single sizes between two runs of the same sweep, profiles/r02l_bench_ab2.txt).
+    // Measured (profiles/r02m_carveout.txt): asking for the largest shared-memory carve-out costs the sweep a
+    // sixth of its throughput (0.957 -> 0.79 of the HBM peak) -- the kernels live on their L1 (half-line rows
+    // shared by neighbouring CTAs, twiddle tables) -- and does not move the sizes in question.  The preference
+    // stays a switch, OFF by default: BBFFT_CUDA_CARVEOUT=1.
+    static const bool carve = [] {
+        char const *e = std::getenv("BBFFT_CUDA_CARVEOUT");
+        return e && *e == '1';
+    }();
+    if (carve && smem_bytes > 0) {
+        BBFFT_CUDA_CHECK(cudaFuncSetAttribute(reinterpret_cast<const void *>(k),
+                                              cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              int(cudaSharedmemCarveoutMaxShared)));
+    }
     return k;
 }
 
