@@ -39,6 +39,36 @@ BUILTIN_DESCRIPTORS = (
 )
 
 
+# Sweep sizes whose kernel is built by NVRTC instead of nvcc.  The two front ends hand ptxas different PTX for
+# the same stub (e.g. 1400 against 1368 instructions for fp64 N=294) and the result differs by up to 13 % per
+# kernel, in either direction, at equal speed over the whole sweep (profiles/r02n_jit_vs_aot.txt: the sweep with
+# the nvcc bundle against BBFFT_CUDA_NO_BUILTIN=1, twice each).  Listed here: the sizes where the NVRTC build won
+# both repetitions by more than 2 %, and the entries of csrc/wisdom.inc that were chosen from NVRTC-built
+# candidates inside the sweep (tools/bench_ab.py).  Arithmetic is unaffected: every multiply is an explicit-
+# rounding intrinsic, a GPU test pins nvcc == NVRTC bit for bit.
+NVRTC_BUILT = {4: (2, 147, 150, 384),
+               8: (54, 90, 96, 100, 112, 120, 128, 160, 175, 243, 245, 294, 315, 343, 392, 490)}
+
+
+def compile_single_nvrtc(descriptor, out_path):
+    """One kernel, one translation unit, NVRTC: byte for byte what plan creation would JIT (code generation is
+    sensitive to the translation unit as well: the same stub compiled next to others comes out differently)."""
+    d = capi.describe(capi.parse_descriptor(descriptor))
+    src_copy = os.path.splitext(out_path)[0] + ".cu"
+    if not os.path.exists(src_copy) or open(src_copy).read() != d["source"] or not os.path.exists(out_path):
+        with open(src_copy, "w") as f:
+            f.write(d["source"])
+        saved = {k: os.environ.pop(k, None) for k in ("BBFFT_CUDA_KERNEL_CACHE", "BBFFT_CUDA_JIT_LINEINFO")}
+        try:
+            with open(out_path, "wb") as f:
+                f.write(capi.compile_to_cubin(d["source"]))
+        finally:
+            for k, v in saved.items():
+                if v is not None:
+                    os.environ[k] = v
+    return d["identifier"]
+
+
 def compile_bundle(descriptors, out_path, verbose=False):
     """descriptors -> cubin at out_path (nvcc, sm_100a); returns the kernel names inside."""
     cfgs = [capi.parse_descriptor(d) for d in descriptors]
@@ -60,7 +90,9 @@ def build_builtin(verbose=False, jobs=8):
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     header = os.path.join(KERNELS, "bbfft_kernels.cuh")
-    chunks = [BUILTIN_DESCRIPTORS[i::jobs] for i in range(jobs)]
+    rtc = ["%scfo16.%d*%d" % ("s" if fp == 4 else "d", n, sweep_k(n, fp)) for fp in (4, 8) for n in NVRTC_BUILT[fp]]
+    nvcc_built = [d for d in BUILTIN_DESCRIPTORS if d not in rtc]
+    chunks = [nvcc_built[i::jobs] for i in range(jobs)]
     procs = []
     all_names = []
     for i, chunk in enumerate(chunks):
@@ -70,6 +102,12 @@ def build_builtin(verbose=False, jobs=8):
         names, proc = compile_bundle(chunk, out, verbose)
         all_names += names
         procs.append((out, proc))
+    for desc in rtc:
+        rtc_out = os.path.join(bdir, "builtin_kernels_rtc_%s.cubin" % desc.split("*")[0].replace(".", "_"))
+        if os.path.exists(rtc_out) and os.path.getmtime(rtc_out) < os.path.getmtime(header):
+            os.remove(rtc_out)
+        all_names.append(compile_single_nvrtc(desc, rtc_out))
+        procs.append((rtc_out, None))
     for out, proc in procs:
         if proc is not None and proc.wait() != 0:
             raise RuntimeError("nvcc failed for " + out)
