@@ -47,7 +47,7 @@ BUILTIN_DESCRIPTORS = (
 # candidates inside the sweep (tools/bench_ab.py).  Arithmetic is unaffected: every multiply is an explicit-
 # rounding intrinsic, a GPU test pins nvcc == NVRTC bit for bit.
 NVRTC_BUILT = {4: (2, 147, 150, 384),
-               8: (54, 90, 96, 100, 112, 120, 128, 160, 175, 243, 245, 294, 315, 343, 392, 490)}
+               8: (54, 90, 96, 100, 112, 120, 128, 160, 175, 243, 245, 250, 294, 315, 343, 392, 405, 448, 490)}
 
 
 def compile_single_nvrtc(descriptor, out_path):
@@ -91,6 +91,8 @@ def build_builtin(verbose=False, jobs=8):
     os.makedirs(bdir, exist_ok=True)
     header = os.path.join(KERNELS, "bbfft_kernels.cuh")
     rtc = ["%scfo16.%d*%d" % ("s" if fp == 4 else "d", n, sweep_k(n, fp)) for fp in (4, 8) for n in NVRTC_BUILT[fp]]
+    # config 3: chosen among 817 NVRTC-built candidates per placement (tools/cases_c3.json): ship what was measured
+    rtc += ["srfo256*1048576", "srfi256*1048576", "srbo256*1048576", "srbi256*1048576"]
     nvcc_built = [d for d in BUILTIN_DESCRIPTORS if d not in rtc]
     chunks = [nvcc_built[i::jobs] for i in range(jobs)]
     procs = []

@@ -30,7 +30,9 @@ def main():
     for rnd in range(2):  # two rounds: every set is measured twice, in alternating order
         for s in (range(nsets) if rnd == 0 else reversed(range(nsets))):
             ov = ";".join("%d:%d:%s" % (fp, n, c[min(s, len(c) - 1)]) for (fp, n), c in CAND.items())
-            env = dict(os.environ, BBFFT_CUDA_WISDOM_OVERRIDE=ov, BBFFT_CUDA_JIT_LINEINFO="0",
+            # every kernel of the sweep NVRTC-built, one per translation unit: candidates and incumbents in the
+            # same build flavor (aot.py: NVRTC_BUILT must list the sizes whose winner is adopted from here)
+            env = dict(os.environ, BBFFT_CUDA_WISDOM_OVERRIDE=ov, BBFFT_CUDA_JIT_LINEINFO="0", BBFFT_CUDA_NO_BUILTIN="1",
                        BBFFT_CUDA_KERNEL_CACHE=os.path.join(ROOT, "kcache"))
             path = os.path.join(out_dir, "bench_ab_%d_%d.csv" % (rnd, s))
             subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "4", "--warmup", "3", "--no-extra",
