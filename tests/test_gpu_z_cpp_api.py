@@ -23,6 +23,45 @@ def _build():
                            "-Wl,-rpath," + LIBDIR])
 
 
+REPRO = os.path.join(ROOT, "tests", "cpp", "repro_c2r")
+
+
+def _build_repro():
+    src = os.path.join(ROOT, "tests", "cpp", "repro_c2r.cpp")
+    deps = [src, os.path.join(LIBDIR, "libbbfft_cuda.so")]
+    if os.path.exists(REPRO) and all(os.path.getmtime(REPRO) >= os.path.getmtime(d) for d in deps):
+        return
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                           "-I" + os.path.join(CUDA_HOME, "include"), src, "-o", REPRO, "-L" + LIBDIR, "-lbbfft_cuda",
+                           "-L" + os.path.join(CUDA_HOME, "lib64"), "-lcudart_static", "-ldl", "-lrt", "-lpthread",
+                           "-Wl,-rpath," + LIBDIR])
+
+
+def test_soak_harness_compiles(pkg):
+    _build_repro()
+    assert os.path.exists(REPRO)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [
+    # the round-1 wrong result: fp64 c2r M=32 N=424 (4 x 53 half length), fresh plans and one re-used plan, user
+    # streams of both kinds; every execute against a host long-double DFT and bit-identical to the first
+    ["c2r", "f64", "32", "424", "4", "40", "fresh", "blocking"],
+    ["c2r", "f64", "32", "424", "4", "300", "reuse", "nonblocking"],
+    ["c2r", "f32", "32", "424", "4", "100", "reuse", "blocking"],
+    ["r2c", "f64", "32", "848", "4", "100", "reuse", "nonblocking"],
+    ["c2c", "f64", "16", "490", "16", "100", "reuse", "default"],
+    ["c2c", "f32", "16", "509", "8", "50", "reuse", "blocking"],
+])
+def test_determinism_soak(pkg, args):
+    """tests/cpp/repro_c2r: repeated executes from C++ user code (the environment the round-1 failure needed)."""
+    _build_repro()
+    r = subprocess.run([REPRO] + args, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and "0 bad iterations" in r.stdout, r.stdout[-2000:] + r.stderr[-1000:]
+
+
 def test_cpp_api_user_code_compiles(pkg):
     """User code written against the reference's headers (configuration aggregate init,
     make_plan, execute overloads, caches, generator) builds against include/bbfft."""
