@@ -114,6 +114,25 @@ BBK_DEV double ffma(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 template <class T> BBK_DEV cx<T> operator+(cx<T> a, cx<T> b) { return cx<T>{a.x + b.x, a.y + b.y}; }
 template <class T> BBK_DEV cx<T> operator-(cx<T> a, cx<T> b) { return cx<T>{a.x - b.x, a.y - b.y}; }
+#if defined(BBK_F32X2) && !defined(BBFFT_EMU)
+// Packed fp32 arithmetic of sm_100 (add.f32x2 -> SASS FADD2): a complex add is ONE issue slot.  Same rounding
+// as two scalar adds, so results do not change; what changes is the number of instructions the four
+// schedulers of an SM have to issue, which is what bounds the fp32 tile kernels.
+BBK_DEV cx<float> operator+(cx<float> a, cx<float> b) {
+    cx<float> r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+BBK_DEV cx<float> operator-(cx<float> a, cx<float> b) {
+    cx<float> r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+#endif
 template <class T> BBK_DEV cx<T> cmul(cx<T> a, cx<T> b) {
     return cx<T>{ffma(a.x, b.x, -fmul(a.y, b.y)), ffma(a.x, b.y, fmul(a.y, b.x))};
 }
@@ -1388,7 +1407,7 @@ template <class C> BBK_DEV void fft1d(args const &a) {
 // writes through the digit reversal ("sorted") so that pass B sees natural order -- every thread
 // holds its sub-FFTs in registers across one extra barrier instead of a second tile buffer.
 // ------------------------------------------------------------------------------------------
-enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2, T_DSMEM = 3 };
+enum : int { T_GLOBAL = 0, T_SMEM = 1, T_SMEM_SORTED = 2, T_DSMEM = 3, T_STAGED = 4, T_GLOBAL_REAL = 5 };
 
 // Thread-block cluster primitives (sm_90+): the barrier over all CTAs of the cluster and a load from
 // another CTA's shared memory (distributed shared memory) by shared-window offset.
@@ -1422,6 +1441,9 @@ BBK_DEV cx<double> ld_cluster(const cx<double> *sm, int idx, unsigned rank) {
 // the data while the issuing warps go on computing; cp.async.wait_group + a CTA barrier publish it.
 #ifdef BBFFT_EMU
 template <class SP, class E> BBK_DEV void async_copy_elem(SP sm, int phys, const E *src) { sm[phys] = *src; }
+template <class SP, class E> BBK_DEV void async_copy_16(SP sm, int phys, const E *src) {
+    for (int i = 0; i < int(16 / sizeof(E)); ++i) sm[phys + i] = src[i];
+}
 BBK_DEV void async_commit() {}
 BBK_DEV void async_wait_all() {}
 #else
@@ -1434,8 +1456,58 @@ template <class E> BBK_DEV void async_copy_elem(E *sm, int phys, const E *src) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
 }
+// 16 bytes at once (two complex<float> or one complex<double>); both addresses 16-byte aligned
+template <class E> BBK_DEV void async_copy_16(E *sm, int phys, const E *src) {
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(sm + phys));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 BBK_DEV void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 BBK_DEV void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
+// Bulk asynchronous copies (cp.async.bulk, the TMA unit without a tensor map: SASS UBLKCP) completing on an
+// mbarrier in shared memory.  One thread issues them; everybody waits on the barrier's phase.  The wait is
+// bounded: a kernel that would spin forever traps instead.
+#ifdef BBFFT_EMU
+template <class SP> BBK_DEV void mbar_init(SP, int) {}
+template <class SP> BBK_DEV void mbar_expect(SP, int, unsigned) {}
+template <class SP, class E> BBK_DEV void bulk_copy(SP sm, int phys, const E *src, unsigned bytes, int) {
+    for (unsigned i = 0; i < bytes / sizeof(E); ++i) sm[phys + int(i)] = src[i];
+}
+template <class SP> BBK_DEV void mbar_wait(SP, int, unsigned) {}
+#else
+template <class E> BBK_DEV void mbar_init(E *sm, int bar) {
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(sm + bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+template <class E> BBK_DEV void mbar_expect(E *sm, int bar, unsigned bytes) {
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(sm + bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+template <class E> BBK_DEV void bulk_copy(E *sm, int phys, const E *src, unsigned bytes, int bar) {
+    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(sm + phys));
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(sm + bar));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+template <class E> BBK_DEV void mbar_wait(E *sm, int bar, unsigned phase) {
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(sm + bar));
+    unsigned done = 0;
+    u64 t0 = 0;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(b), "r"(phase)
+                     : "memory");
+        if (done) break;
+        u64 now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) __trap(); // four seconds: the copy this phase waits for was never issued
+    }
+}
 #endif
 
 template <class C> BBK_DEV int tile_phys(int lin) {
@@ -1446,10 +1518,53 @@ template <class C> BBK_DEV int tile_phys(int lin) {
     }
 }
 
+// Offsets inside the padded tile that are compile-time constants.  A stage touches `R` elements at stride A
+// from a base element; tile_phys(base + A j) - tile_phys(base) does not depend on the base when
+//   * the tile is unpadded, or
+//   * A is a multiple of PADK (every step crosses A / PADK pads), or
+//   * A divides PADK and the base sits less than A behind a multiple of PADK (SPAN and SN, the periods of the
+//     base in the stage's sub-FFT index and in the outer index, are multiples of PADK): j steps cross
+//     j / (PADK / A) pads.
+// Then one address per sub-FFT is computed and the rest are immediates of the LDS / STS instructions
+// (a third of the tile kernel's instructions were such index arithmetic).
+template <class C, int A, int SPAN, int SN> struct pad_rule {
+    static constexpr int PK = C::PADK;
+    static constexpr bool linear = PK == 0;
+    static constexpr bool r1 = PK > 0 && A % (PK > 0 ? PK : 1) == 0;
+    static constexpr bool r3 = PK > 0 && !r1 && PK % A == 0 && SPAN % (PK > 0 ? PK : 1) == 0 && SN % (PK > 0 ? PK : 1) == 0;
+    static constexpr bool ok = linear || r1 || r3;
+    static BBK_CE int off(int j) {
+        return linear ? A * j : r1 ? A * j + A * j / (PK > 0 ? PK : 1) : A * j + j / ((PK > 0 ? PK : 1) / A);
+    }
+};
+
 template <class P> BBK_CE int pass_ns(int s) {
     int n = P::N;
     for (int i = 0; i < s; ++i) n /= P::radix(i);
     return n;
+}
+
+// Real rows of the fused r2c / c2r tiles (C::REAL): complex element `pos` of the half-length transform of
+// batch lane m is the pair of reals (2 pos, 2 pos + 1) of the row, M reals apart.  M == 1: the pair is one
+// aligned complex word (the host checks the pointer, plan.cpp), otherwise two coalesced scalar accesses.
+template <class C> BBK_DEV cx<typename C::real_t> ld_real_pair(const void *in, u64 row, int m, int pos) {
+    using T = typename C::real_t;
+    const T *BBK_RESTRICT x = reinterpret_cast<const T *>(in) + row;
+    if constexpr (C::PA::S == 1) {
+        return reinterpret_cast<const cx<T> *>(x)[pos];
+    } else {
+        return cx<T>{x[m + C::PA::S * (2 * pos)], x[m + C::PA::S * (2 * pos + 1)]};
+    }
+}
+template <class C> BBK_DEV void st_real_pair(void *out, u64 row, int m, int pos, cx<typename C::real_t> v) {
+    using T = typename C::real_t;
+    T *BBK_RESTRICT x = reinterpret_cast<T *>(out) + row;
+    if constexpr (C::PA::S == 1) {
+        reinterpret_cast<cx<T> *>(x)[pos] = v;
+    } else {
+        x[m + C::PA::S * (2 * pos)] = v.x;
+        x[m + C::PA::S * (2 * pos + 1)] = v.y;
+    }
 }
 
 // `after_loads` runs when every thread of the CTA holds its inputs of the stage in registers; the
@@ -1472,6 +1587,7 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
     constexpr int CNT = (TOTAL + C::THREADS - 1) / C::THREADS;
     constexpr bool LAST = (S == P::L - 1);
     static_assert(DST == T_SMEM || LAST, "only a pass's last stage leaves the in-place scheme");
+    static_assert(SRC != T_STAGED || P::PITCH == P::S * P::N, "the staging buffer holds packed rows");
     using WR = typename P::template WR<S>;
     const cx<T> *BBK_RESTRICT tw = reinterpret_cast<const cx<T> *>(a.tw) + P::tw_off(S);
 
@@ -1483,14 +1599,29 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
             const int lo = id % P::S, r = id / P::S;
             const int u = r % NSUB, hi = r / NSUB;
             const int pos0 = (u / NS1) * NS + u % NS1; // position along the axis of input j = 0
-            const int base = lo + P::S * pos0 + P::S * P::N * hi;
+            const int base = lo + P::S * pos0 + P::PITCH * hi;
+            using LR = pad_rule<C, P::S * NS1, P::S * NS, P::PITCH>;
+            [[maybe_unused]] const int pb = tile_phys<C>(base);
             static_for<0, R>([&](auto jj) {
                 constexpr int j = decltype(jj)::value;
                 [[maybe_unused]] const int lin = base + P::S * NS1 * j;
+                [[maybe_unused]] const int phys = LR::ok ? pb + LR::off(j) : tile_phys<C>(lin);
                 if constexpr (SRC == T_GLOBAL) {
                     // (P::GS: element stride of the axis in global memory; differs from the shared-memory
                     // stride P::S only for the cluster kernel's column pass)
-                    v[i][j] = C::ld(a.in, gbase + u64(lo + P::GS * (pos0 + NS1 * j) + P::GS * P::N * hi));
+                    v[i][j] = C::ld(a.in, gbase + u64(lo + P::GS * (pos0 + NS1 * j) + P::GPITCH * hi));
+                    if constexpr (C::REAL == 2) {
+                        // c2r tile, column pass: the tile holds N1/2 columns; column 0 carries the spectrum columns
+                        // 0 and N1/2 -- both transform to REAL columns -- as one complex column X0 + i XH
+                        if (lo < C::PA::S) {
+                            const cx<T> xh = C::ld(a.in, gbase + u64(lo + C::PA::S * C::PA::N + P::GS * (pos0 + NS1 * j)));
+                            v[i][j] = cx<T>{v[i][j].x - xh.y, v[i][j].y + xh.x};
+                        }
+                    }
+                } else if constexpr (SRC == T_GLOBAL_REAL) {
+                    // r2c tile, first stage of the half-length pass: complex element `pos` of a row is the pair of
+                    // reals (2 pos, 2 pos + 1); `gbase` and C::RROW (row pitch) count reals
+                    v[i][j] = ld_real_pair<C>(a.in, gbase + u64(C::RROW) * u64(hi), lo, pos0 + NS1 * j);
                 } else if constexpr (SRC == T_DSMEM) {
                     // cluster kernel, first stage of the column pass: row n2 of the tile lives in the shared
                     // memory of CTA n2 / N2L in the row-pass layout  m + M (n1 + N1 n2l);  this CTA owns the
@@ -1498,8 +1629,12 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
                     const int n2 = pos0 + NS1 * j;
                     const int owner = n2 / C::N2L, n2l = n2 % C::N2L;
                     v[i][j] = ld_cluster(sm, tile_phys<C>(lo + int(rank) * P::S + C::ROWLEN * n2l), unsigned(owner));
+                } else if constexpr (SRC == T_STAGED) {
+                    // staged kernel, first stage of pass A: the leading C::STG elements of the tile wait in
+                    // the (unpadded) staging buffer behind the tile, the rest already sits in place
+                    v[i][j] = lin < C::STG ? sm[C::STG_OFF + lin] : sm[phys];
                 } else {
-                    v[i][j] = sm[tile_phys<C>(lin)];
+                    v[i][j] = sm[phys];
                 }
             });
         }
@@ -1511,8 +1646,9 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
         cluster_sync(); // every CTA of the cluster has gathered its columns: the row-pass layout is dead everywhere
     }
     if constexpr (HOOK::active) {
-        static_assert(SRC == T_SMEM && DST == T_GLOBAL, "the hook belongs to the stage that empties shared memory");
-        BBK_SYNC(); // the tile has left shared memory
+        static_assert((SRC == T_SMEM && DST == T_GLOBAL) || SRC == T_STAGED,
+                      "the hook belongs to a stage that empties (a part of) shared memory");
+        BBK_SYNC(); // the tile (or the staging buffer) has left shared memory
         after_loads();
     }
     static_for<0, CNT>([&](auto ii) {
@@ -1530,20 +1666,37 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
                 });
             }
             if constexpr (DST == T_SMEM) {
-                const int base = lo + P::S * ((u / NS1) * NS + u % NS1) + P::S * P::N * hi;
+                const int base = lo + P::S * ((u / NS1) * NS + u % NS1) + P::PITCH * hi;
+                using SR = pad_rule<C, P::S * NS1, P::S * NS, P::PITCH>;
+                const int pb = tile_phys<C>(base);
                 static_for<0, R>([&](auto qq) {
                     constexpr int q = decltype(qq)::value;
-                    sm[tile_phys<C>(base + P::S * NS1 * q)] = v[i][q];
+                    sm[SR::ok ? pb + SR::off(q) : tile_phys<C>(base + P::S * NS1 * q)] = v[i][q];
                 });
             } else {
                 const int bin0 = bin_of_sub<P>(u);
-                [[maybe_unused]] const int base = lo + P::S * bin0 + P::S * P::N * hi;
+                [[maybe_unused]] const int base = lo + P::S * bin0 + P::PITCH * hi;
+                // (bin0 < N / R: the base sits less than the stride S N / R behind a multiple of the row pitch)
+                using SR = pad_rule<C, P::S * (P::N / R), C::PADK, P::PITCH>;
+                [[maybe_unused]] const int pb = (DST == T_GLOBAL || DST == T_GLOBAL_REAL) ? 0 : tile_phys<C>(base);
                 static_for<0, R>([&](auto qq) {
                     constexpr int q = decltype(qq)::value;
                     if constexpr (DST == T_GLOBAL) {
-                        C::st(a.out, gbase + u64(lo + P::GS * (bin0 + (P::N / R) * q) + P::GS * P::N * hi), v[i][q]);
+                        if constexpr (C::REAL == 1) {
+                            // r2c tile: column 0 is the packed pair of the real columns 0 and N1/2; its transform is
+                            // unpacked from the scratch column behind the tile (tile_r2c_unpack)
+                            if (lo < C::PA::S) {
+                                sm[C::SCR_OFF + lo + C::PA::S * (bin0 + (P::N / R) * q)] = v[i][q];
+                            } else {
+                                C::st(a.out, gbase + u64(lo + P::GS * (bin0 + (P::N / R) * q)), v[i][q]);
+                            }
+                        } else {
+                            C::st(a.out, gbase + u64(lo + P::GS * (bin0 + (P::N / R) * q) + P::GPITCH * hi), v[i][q]);
+                        }
+                    } else if constexpr (DST == T_GLOBAL_REAL) {
+                        st_real_pair<C>(a.out, gbase + u64(C::RROW) * u64(hi), lo, bin0 + (P::N / R) * q, v[i][q]);
                     } else {
-                        sm[tile_phys<C>(base + P::S * (P::N / R) * q)] = v[i][q];
+                        sm[SR::ok ? pb + SR::off(q) : tile_phys<C>(base + P::S * (P::N / R) * q)] = v[i][q];
                     }
                 });
             }
@@ -1627,6 +1780,221 @@ template <class C> BBK_DEV void fft2d_tile_persistent(args const &a) {
     }
 }
 
+// Staged variant of the persistent kernel (C::STG > 0; grid = resident CTAs).  The pipeline above can only
+// start the next tile's copies when the current tile has left shared memory, i.e. it hides them behind ONE
+// stage; through the other stages of a 128 KiB tile (one CTA per SM) nothing is in flight, and those stages
+// are bound by shared-memory bandwidth (six trips of the tile = 3.3 us against 5.9 us of HBM time per tile
+// and SM).  Here the shared memory left beside the tile is a staging buffer for the leading C::STG elements
+// (whole rows of pass A) of the NEXT tile: their copies are issued as soon as the first stage of pass A has
+// pulled the current tile's share out of the buffer, and land while ALL remaining stages run; only the
+// rest (a quarter of a 128 x 128 fp32 tile) waits, as before, for the last stage of pass B.  The staging
+// buffer is unpadded (the first stage reads it with unit stride along the lanes), so its copies move 16 bytes.
+template <class C> struct stage_loader {
+    static constexpr bool active = true;
+    using T = typename C::real_t;
+    args const &a;
+    BBK_SPTR(cx<T>) sm;
+    u64 tile; // the tile to fetch (>= a.K: nothing)
+    int tid;
+    bool bulk; // C::BULK and the tiles are 16-byte aligned: one thread hands the copy to the TMA unit
+    BBK_DEV void operator()() const {
+        if (tile < a.K) {
+            const cx<T> *BBK_RESTRICT src = reinterpret_cast<const cx<T> *>(a.in) + tile * u64(C::TILE_STRIDE);
+            constexpr int PER = 16 / int(sizeof(cx<T>)); // elements per 16-byte copy
+            if (bulk) {
+                if (tid == 0) {
+                    constexpr int CHUNK = 8192 / int(sizeof(cx<T>)); // elements per bulk copy
+                    mbar_expect(sm, C::STG_OFF + C::STG, unsigned(C::STG * sizeof(cx<T>)));
+                    for (int lin = 0; lin < C::STG; lin += CHUNK) {
+                        const int cnt = C::STG - lin < CHUNK ? C::STG - lin : CHUNK;
+                        bulk_copy(sm, C::STG_OFF + lin, src + lin, unsigned(cnt * sizeof(cx<T>)), C::STG_OFF + C::STG);
+                    }
+                }
+            } else if (PER == 1 || (reinterpret_cast<u64>(src) & 15) == 0) {
+                for (int lin = tid * PER; lin < C::STG; lin += C::THREADS * PER) async_copy_16(sm, C::STG_OFF + lin, src + lin);
+            } else {
+                for (int lin = tid; lin < C::STG; lin += C::THREADS) async_copy_elem(sm, C::STG_OFF + lin, src + lin);
+            }
+        }
+        async_commit();
+    }
+};
+template <class C> struct rest_loader {
+    static constexpr bool active = true;
+    using T = typename C::real_t;
+    args const &a;
+    BBK_SPTR(cx<T>) sm;
+    u64 tile;
+    int tid;
+    BBK_DEV void operator()() const {
+        if (tile < a.K) {
+            const cx<T> *BBK_RESTRICT src = reinterpret_cast<const cx<T> *>(a.in) + tile * u64(C::TILE_STRIDE);
+            constexpr int TILE = C::PA::S * C::PA::N * C::PA::O;
+            for (int lin = C::STG + tid; lin < TILE; lin += C::THREADS) async_copy_elem(sm, tile_phys<C>(lin), src + lin);
+        }
+        async_commit();
+    }
+};
+
+template <class C> BBK_DEV void fft2d_tile_staged(args const &a) {
+    using T = typename C::real_t;
+    using PA = typename C::PA;
+    static_assert(C::STG % 2 == 0 && C::STG_OFF % 2 == 0, "16-byte copies into the staging buffer");
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const u64 step = BBK_NCTAS();
+    u64 tile = BBK_BID();
+    // (C::BULK: the mbarrier sits behind the staging buffer)
+    const bool bulk = C::BULK && (reinterpret_cast<u64>(a.in) & 15) == 0 && (u64(C::TILE_STRIDE) * sizeof(cx<T>)) % 16 == 0;
+    unsigned phase = 0;
+    if (bulk) {
+        if (tid == 0) mbar_init(sm, C::STG_OFF + C::STG);
+        BBK_SYNC();
+    }
+    stage_loader<C>{a, sm, tile, tid, bulk}();
+    rest_loader<C>{a, sm, tile, tid}();
+    for (; tile < a.K; tile += step) {
+        const u64 gbase = tile * u64(C::TILE_STRIDE);
+        async_wait_all();
+        if (bulk) {
+            mbar_wait(sm, C::STG_OFF + C::STG, phase);
+            phase ^= 1u;
+        }
+        BBK_SYNC(); // every thread's copies have landed
+        constexpr int DST0 = PA::L == 1 ? T_SMEM_SORTED : T_SMEM;
+        tile_stage<C, PA, 0, T_STAGED, DST0, stage_loader<C>>(a, sm, gbase, tid, stage_loader<C>{a, sm, tile + step, tid, bulk});
+        tile_pass<C, PA, 1, T_SMEM, T_SMEM_SORTED>(a, sm, gbase, tid);
+        BBK_SYNC();
+        tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL, rest_loader<C>>(a, sm, gbase, tid,
+                                                                          rest_loader<C>{a, sm, tile + step, tid});
+    }
+}
+
+// Fused real 2d tiles (C::REAL = 1: r2c, 2: c2r; even N1).  The reference runs a real nd transform as one
+// double-batched launch per mode (src/common/algorithm/nd_fft.hpp:66-152: r2c along n1, then c2c along n2 over
+// the N1/2+1 spectrum columns): two HBM round trips.  Here one CTA owns one transform and its tile holds
+// H = N1/2 complex columns:
+//   r2c: the real rows are read as H complex words per row and transformed along n1 (half-length pass A); the
+//        split  X[i] = A + B, X[H-i] = conj(A - B)  (the arithmetic of the 1d kernel's r2c_last_stage) runs in
+//        place on the pairs (i, H - i); the columns 0 and H of the n1-spectrum are REAL, so they share tile
+//        column 0 as X0 + i XH; pass B transforms the H columns along n2 and stores columns 1 .. H-1; the
+//        transform of column 0 goes to a scratch column and is unpacked by conjugate symmetry,
+//        F0[k] = (Z[k] + conj Z[N2-k]) / 2, FH[k] = (Z[k] - conj Z[N2-k]) / 2i, into the spectrum columns 0 and H;
+//   c2r: the mirror image -- pass B loads column 0 as X0 + i XH (both are spectra of real columns), the merge
+//        z[i] = A + B, z[H-i] = conj(A - B) runs on the pairs, half-length pass A stores real pairs.  Like every
+//        nd c2r (cuFFT, MKL) this assumes the conjugate-even spectrum of a real signal.
+// The tile is a power-of-two H x N2 block for power-of-two sizes (no ragged N1/2+1 columns), HBM traffic is one
+// read of the real tile and one write of the spectrum tile (or the reverse), and in place works because every
+// global load of the CTA precedes its first global store (barriers in between).
+template <class C, bool FORWARD_SPLIT> BBK_DEV void tile_real_pairs(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int tid) {
+    using T = typename C::real_t;
+    using PA = typename C::PA;
+    constexpr int H = PA::N;           // half length: complex columns of the tile
+    constexpr int M = PA::S;
+    constexpr int UNITS = H / 2 + 1;   // pairs (i, H - i), i = 1 .. H/2, and the packed column 0
+    constexpr int TOTAL = M * UNITS * PA::O;
+    constexpr int CNT = (TOTAL + C::THREADS - 1) / C::THREADS;
+    const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+    static_for<0, CNT>([&](auto ii) {
+        constexpr int c = decltype(ii)::value;
+        const int id = tid + C::THREADS * c;
+        if (TOTAL % C::THREADS == 0 || id < TOTAL) {
+            const int lo = id % M, r = id / M;
+            const int i = r % UNITS, hi = r / UNITS;
+            const int row = lo + PA::PITCH * hi;
+            const int pi = tile_phys<C>(row + M * i);
+            if (i == 0) {
+                // r2c: y0 = (a, b) -> X[0] = a + b, X[H] = a - b (both real), kept as one complex number;
+                // c2r: (X0, XH) -> z0 = (X0 + XH, X0 - XH): the same map
+                const cx<T> y = sm[pi];
+                sm[pi] = cx<T>{y.x + y.y, y.x - y.y};
+            } else {
+                const int pn = tile_phys<C>(row + M * (H - i));
+                const cx<T> w = ldg_cx(twr + i);
+                const cx<T> iw = cx<T>{-w.y, w.x};
+                const cx<T> yi = sm[pi];
+                const cx<T> yn = sm[pn];
+                if constexpr (FORWARD_SPLIT) {
+                    const cx<T> y2 = conj(yn);
+                    const cx<T> aa = rmul(y2 + yi, T(0.5));
+                    const cx<T> bb = cmul(rmul(y2 - yi, T(0.5)), iw);
+                    sm[pi] = aa + bb;
+                    if (2 * i != H) sm[pn] = conj(aa - bb);
+                } else {
+                    const cx<T> x2 = conj(yn);
+                    const cx<T> aa = yi + x2;
+                    const cx<T> bb = cmul(yi - x2, iw);
+                    sm[pi] = aa + bb;
+                    if (2 * i != H) sm[pn] = conj(aa - bb);
+                }
+            }
+        }
+    });
+}
+
+// r2c: the transform Z of the packed column X0 + i XH sits in the scratch column (natural order); unpack it into
+// the spectrum columns 0 and H of the output tile.
+template <class C> BBK_DEV void tile_r2c_unpack(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 cbase, int tid) {
+    using T = typename C::real_t;
+    constexpr int M = C::PA::S, H = C::PA::N, N2 = C::PB::N;
+    constexpr int UNITS = N2 / 2 + 1; // pairs (k, N2 - k)
+    constexpr int TOTAL = M * UNITS;
+    for (int id = tid; id < TOTAL; id += C::THREADS) {
+        const int lo = id % M, k = id / M;
+        const int kn = (N2 - k) % N2;
+        const cx<T> zk = sm[C::SCR_OFF + lo + M * k];
+        const cx<T> zr = sm[C::SCR_OFF + lo + M * kn];
+        const cx<T> zn = conj(zr);
+        const cx<T> f0 = rmul(zk + zn, T(0.5));
+        const cx<T> d = rmul(zk - zn, T(0.5));
+        const cx<T> fh = cx<T>{d.y, -d.x}; // d / i
+        const u64 o = cbase + u64(lo) + u64(C::PB::GS) * u64(k);
+        C::st(a.out, o, f0);
+        C::st(a.out, o + u64(M * H), fh);
+        if (kn != k) {
+            const u64 on = cbase + u64(lo) + u64(C::PB::GS) * u64(kn);
+            C::st(a.out, on, conj(f0));
+            C::st(a.out, on + u64(M * H), conj(fh));
+        }
+    }
+}
+
+template <class C> BBK_DEV void fft2d_tile_real_cta(args const &a, const u64 tile) {
+    using T = typename C::real_t;
+    BBK_SPTR(cx<T>) sm = sptr<cx<T>>(BBK_SMEM());
+    const int tid = BBK_TID();
+    const u64 cbase = tile * u64(C::TILE_STRIDE); // spectrum tile, complex elements
+    const u64 rbase = tile * u64(C::RTS);         // real tile, reals
+    if constexpr (C::REAL == 1) {
+        tile_pass<C, typename C::PA, 0, T_GLOBAL_REAL, T_SMEM_SORTED>(a, sm, rbase, tid);
+        BBK_SYNC();
+        tile_real_pairs<C, true>(a, sm, tid);
+        BBK_SYNC();
+        tile_pass<C, typename C::PB, 0, T_SMEM, T_GLOBAL>(a, sm, cbase, tid);
+        BBK_SYNC();
+        tile_r2c_unpack<C>(a, sm, cbase, tid);
+    } else {
+        tile_pass<C, typename C::PB, 0, T_GLOBAL, T_SMEM_SORTED>(a, sm, cbase, tid);
+        BBK_SYNC();
+        tile_real_pairs<C, false>(a, sm, tid);
+        BBK_SYNC();
+        if constexpr (C::PA::S == 1) {
+            // M = 1: the last stage of pass A holds digit-reversed positions of a row, i.e. scattered 8-byte stores;
+            // sort into the tile instead and copy the rows out with consecutive threads on consecutive words
+            tile_pass<C, typename C::PA, 0, T_SMEM, T_SMEM_SORTED>(a, sm, rbase, tid);
+            BBK_SYNC();
+            using PA = typename C::PA;
+            constexpr int TILE = PA::N * PA::O;
+            for (int lin = tid; lin < TILE; lin += C::THREADS) {
+                const int pos = lin % PA::N, hi = lin / PA::N;
+                st_real_pair<C>(a.out, rbase + u64(C::RROW) * u64(hi), 0, pos, sm[tile_phys<C>(pos + PA::PITCH * hi)]);
+            }
+        } else {
+            tile_pass<C, typename C::PA, 0, T_SMEM, T_GLOBAL_REAL>(a, sm, rbase, tid);
+        }
+    }
+}
+
 // Cluster variant (C::CL > 1 CTAs per tile, thread-block cluster of CL, distributed shared memory).
 // A 128 x 128 fp32 tile is 128 KiB: one CTA per SM, and a stage-synchronised CTA that is alone on its SM
 // overlaps nothing with its own load latency (round 1: 0.65 of the HBM peak, against 0.96 for the 32 KiB
@@ -1654,8 +2022,14 @@ template <class C> BBK_DEV void fft2d_tile_cluster(args const &a) {
 
 template <class C> BBK_DEV void fft2d_tile(args const &a) {
     pdl_prologue();
-    if constexpr (C::CL > 1) {
+    if constexpr (C::REAL != 0) {
+        const u64 tile = BBK_BID();
+        if (tile >= a.K) return;
+        fft2d_tile_real_cta<C>(a, tile);
+    } else if constexpr (C::CL > 1) {
         fft2d_tile_cluster<C>(a);
+    } else if constexpr (C::STG > 0) {
+        fft2d_tile_staged<C>(a);
     } else if constexpr (C::PERSIST) {
         fft2d_tile_persistent<C>(a);
     } else {

@@ -452,7 +452,9 @@ fft2d_plan::fft2d_plan(problem_2d const &prob, api a, jit_cache *cache, std::str
     : api_(std::move(a)) {
     K_ = prob.K;
     tp_ = plan_kernel_2d(prob, api_.props(), tune);
-    slice_bytes_ = std::size_t(tp_.p.tile_stride) * 2 * std::size_t(prob.fp);
+    in_slice_bytes_ = out_slice_bytes_ = std::size_t(tp_.p.tile_stride) * 2 * std::size_t(prob.fp);
+    if (tp_.p.real == 1) in_slice_bytes_ = std::size_t(tp_.p.real_tile_stride) * std::size_t(prob.fp);
+    if (tp_.p.real == 2) out_slice_bytes_ = std::size_t(tp_.p.real_tile_stride) * std::size_t(prob.fp);
     jit_cache_key key{tp_.identifier, api_.device_id()};
     if (cache) module_ = cache->get(key);
     if (!module_) module_ = builtin_module(tp_.identifier, api_.device());
@@ -475,14 +477,24 @@ fft2d_plan::~fft2d_plan() { api_.release_buffer(twiddle_); }
 
 void fft2d_plan::enqueue(void const *in, void *out, cudaStream_t stream) { enqueue_slab(in, out, 0, K_, stream); }
 
+bool fft2d_plan::pointers_ok(void const *in, void const *out) const {
+    if (tp_.p.real == 0 || tp_.p.M != 1) return true;
+    const std::uintptr_t word = 2 * std::uintptr_t(tp_.p.fp);
+    void const *r = tp_.p.real == 1 ? in : out;
+    return reinterpret_cast<std::uintptr_t>(r) % word == 0;
+}
+
 void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
                               cudaStream_t stream) {
     if (k0 + count > K_) throw bad_configuration("slab exceeds the planned batch");
     if (count == 0) return;
+    if (!pointers_ok(in, out)) {
+        throw bad_configuration("fused real 2d plan: the real tensor must be aligned to a complex number when M = 1");
+    }
     device_guard guard(api_.device());
     kernel_args a = {};
-    a.in = static_cast<char const *>(in) + k0 * slice_bytes_;
-    a.out = static_cast<char *>(out) + k0 * slice_bytes_;
+    a.in = static_cast<char const *>(in) + k0 * in_slice_bytes_;
+    a.out = static_cast<char *>(out) + k0 * out_slice_bytes_;
     a.tw = twiddle_;
     a.K = count;
     a.M = tp_.p.M;
@@ -497,13 +509,18 @@ void fft2d_plan::enqueue_slab(void const *in, void *out, std::uint64_t k0, std::
 
 // Steps of a 2d/3d plan.  c2c transforms in the default layout whose M x N1 x N2 tile fits into
 // shared memory run modes 1 and 2 fused (BBFFT_CUDA_ND_FUSE=0 turns this off: "multi-pass").
-std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain) {
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain, bool fuse_real) {
     std::vector<nd_step> steps;
     const std::uint64_t K = cfg.shape[cfg.dim + 1];
     std::vector<configuration> passes;
     nd_passes(cfg, [&](configuration const &c) { passes.push_back(c); }); // validates the layout, too
     char const *fuse_env = std::getenv("BBFFT_CUDA_ND_FUSE");
-    bool fuse = !(fuse_env && *fuse_env == '0') && cfg.type == transform_type::c2c && cfg.dim >= 2;
+    // real transforms (even N1, default layouts): modes 1 and 2 run as one fused real tile kernel
+    // (bbk::fft2d_tile_real_cta); BBFFT_CUDA_ND_FUSE_REAL=0 keeps one launch per mode.  Not part of a chain.
+    const bool real = cfg.type != transform_type::c2c;
+    char const *fuse_real_env = std::getenv("BBFFT_CUDA_ND_FUSE_REAL");
+    bool fuse = !(fuse_env && *fuse_env == '0') && cfg.dim >= 2;
+    if (real) fuse = fuse && fuse_real && !for_chain && !(fuse_real_env && *fuse_real_env == '0');
     problem_2d t;
     if (fuse) {
         t.fp = static_cast<int>(cfg.fp);
@@ -512,24 +529,34 @@ std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &
         t.N1 = cfg.shape[1];
         t.N2 = cfg.shape[2];
         t.K = (cfg.dim == 3 ? cfg.shape[3] : 1) * K;
-        t.tile_stride = t.M * t.N1 * t.N2;
+        t.tile_stride = t.M * (real ? t.N1 / 2 + 1 : t.N1) * t.N2;
+        if (real) {
+            t.real = cfg.type == transform_type::r2c ? 1 : 2;
+            // (nd_passes accepted the layout: it is one of the two defaults; in place = padded real rows)
+            auto const &rs = cfg.type == transform_type::r2c ? cfg.istride : cfg.ostride;
+            t.inplace = rs[2] == 2 * t.M * (t.N1 / 2 + 1);
+        }
         fuse = tile_fusable(t, dev, for_chain ? 1 : tile_cluster_limit());
     }
-    std::size_t first = 0;
-    if (fuse) {
+    // c2r visits the modes in reverse: the fused tile (modes 2 and 1) is the LAST step
+    const bool tile_last = fuse && cfg.type == transform_type::c2r;
+    auto push_tile = [&] {
         nd_step s;
         s.fused = true;
         s.tile = t;
         s.mult = K ? t.K / K : 0;
         steps.push_back(s);
-        first = 2;
-    }
-    for (std::size_t d = first; d < passes.size(); ++d) {
+    };
+    if (fuse && !tile_last) push_tile();
+    const std::size_t first = (fuse && !tile_last) ? 2 : 0;
+    const std::size_t last = tile_last ? passes.size() - 2 : passes.size();
+    for (std::size_t d = first; d < last; ++d) {
         nd_step s;
         s.pass = passes[d];
         s.mult = K ? passes[d].shape[2] / K : 0;
         steps.push_back(s);
     }
+    if (tile_last) push_tile();
     return steps;
 }
 
@@ -599,20 +626,23 @@ bool nd_plan::try_chain(std::vector<nd_step> const &steps, jit_cache *cache) {
     return true;
 }
 
-nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache) : api_(std::move(a)), dim_(cfg.dim) {
+nd_plan::nd_plan(configuration const &cfg, api a, jit_cache *cache, bool fuse_real)
+    : api_(std::move(a)), dim_(cfg.dim), cfg_(cfg), cache_(cache) {
     K_ = cfg.shape[dim_ + 1];
     char const *chain_env = std::getenv("BBFFT_CUDA_ND_CHAIN");
     const bool want_chain = chain_env && *chain_env == '1';
-    auto steps = nd_decompose(cfg, api_.props(), want_chain);
+    auto steps = nd_decompose(cfg, api_.props(), want_chain, fuse_real);
     chained_ = try_chain(steps, cache);
-    if (want_chain && !chained_) steps = nd_decompose(cfg, api_.props(), false);
+    if (want_chain && !chained_) steps = nd_decompose(cfg, api_.props(), false, fuse_real);
     for (auto const &s : steps) {
         if (chained_) {
             mult_.push_back(s.mult);
             continue;
         }
         if (s.fused) {
-            plans_.push_back(std::make_shared<fft2d_plan>(s.tile, api_, cache));
+            auto tp = std::make_shared<fft2d_plan>(s.tile, api_, cache);
+            if (s.tile.real != 0) real_tile_ = tp; // (r2c: the first step reads `in`; c2r: the last step writes `out`)
+            plans_.push_back(tp);
         } else {
             plans_.push_back(std::make_shared<fft1d_plan>(s.pass, api_, cache));
         }
@@ -659,6 +689,12 @@ unsigned nd_plan::launches_per_execute() const {
 }
 
 void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
+    if (real_tile_ && !real_tile_->pointers_ok(in, out)) {
+        // the user's real tensor is not aligned to a complex number: one launch per mode handles any pointer
+        if (!unfused_) unfused_ = std::make_unique<nd_plan>(cfg_, api_, cache_, false);
+        unfused_->enqueue(in, out, stream);
+        return;
+    }
     void *tmp = tmp_ ? tmp_ : out;
     const std::size_t n = chained_ ? chain_.steps.size() : plans_.size();
     auto src = [&](std::size_t d) { return d == 0 ? in : static_cast<void const *>(tmp); };

@@ -107,19 +107,21 @@ class fft2d_plan : public plan_base {
     tile_plan const &kernel() const { return tp_; }
     void kernel_names(std::vector<std::string> &names) const override { names.push_back(tp_.identifier); }
     std::uint64_t slices() const override { return K_; }
-    std::size_t in_slice_bytes() const override { return slice_bytes_; }
-    std::size_t out_slice_bytes() const override { return slice_bytes_; }
+    std::size_t in_slice_bytes() const override { return in_slice_bytes_; }
+    std::size_t out_slice_bytes() const override { return out_slice_bytes_; }
     void enqueue_slab(void const *in, void *out, std::uint64_t k0, std::uint64_t count,
                       cudaStream_t stream) override;
     bool slices_contiguous() const override { return true; }
-    std::size_t in_bytes_required() const override { return slice_bytes_ * K_; }
-    std::size_t out_bytes_required() const override { return slice_bytes_ * K_; }
+    std::size_t in_bytes_required() const override { return in_slice_bytes_ * K_; }
+    std::size_t out_bytes_required() const override { return out_slice_bytes_ * K_; }
+    // fused real tiles with M == 1 read / write the real rows as aligned complex words
+    bool pointers_ok(void const *in, void const *out) const;
 
   private:
     api api_;
     tile_plan tp_;
     std::uint64_t K_ = 0;
-    std::size_t slice_bytes_ = 0;
+    std::size_t in_slice_bytes_ = 0, out_slice_bytes_ = 0;
     shared_handle<module_handle_t> module_;
     cudaKernel_t kernel_ = nullptr;
     void *twiddle_ = nullptr;
@@ -136,11 +138,13 @@ struct nd_step {
     std::uint64_t mult = 1;
 };
 // (for_chain: steps of one persistent chain kernel -- the fused tile must fit a single CTA)
-std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain = false);
+std::vector<nd_step> nd_decompose(configuration const &cfg, device_props const &dev, bool for_chain = false,
+                                  bool fuse_real = true);
 
 class nd_plan : public plan_base {
   public:
-    nd_plan(configuration const &cfg, api a, jit_cache *cache);
+    // fuse_real = false: real transforms as one launch per mode (the fallback of a fused real plan)
+    nd_plan(configuration const &cfg, api a, jit_cache *cache, bool fuse_real = true);
     ~nd_plan() override;
     nd_plan(nd_plan const &) = delete;
     nd_plan &operator=(nd_plan const &) = delete;
@@ -167,6 +171,12 @@ class nd_plan : public plan_base {
     std::uint64_t K_ = 0, kblock_ = 0; // outer batch and its L2 block (in k)
     std::size_t in_required_ = 0, out_required_ = 0;
     void *tmp_ = nullptr;
+    // a fused real tile step with M == 1 needs complex-aligned real pointers; executes with other pointers go
+    // through this plan (one launch per mode), built on first use
+    configuration cfg_;
+    jit_cache *cache_ = nullptr;
+    std::shared_ptr<fft2d_plan> real_tile_;
+    std::unique_ptr<nd_plan> unfused_;
     // chained execution: all steps in one persistent launch (bbk::chain)
     bool try_chain(std::vector<nd_step> const &steps, jit_cache *cache);
     bool chained_ = false;

@@ -753,6 +753,12 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
 // ------------------------------------------------------------------------------------------
 // identifier
 // ------------------------------------------------------------------------------------------
+// experiment switch: packed fp32 adds (add.f32x2) in the kernels of this process (BBFFT_CUDA_F32X2=1)
+static bool packed_f32() {
+    char const *e = std::getenv("BBFFT_CUDA_F32X2");
+    return e && *e == '1';
+}
+
 std::string make_identifier(kernel_params const &p) {
     // K is deliberately not part of the key (reference: jit_cache key = identifier + device,
     // include/bbfft/jit_cache.hpp:23-41; K is a run-time argument)
@@ -768,6 +774,7 @@ std::string make_identifier(kernel_params const &p) {
     if (p.chained) os << "_ch";
     if (!p.cb_load.empty()) os << "_" << p.cb_load;
     if (!p.cb_store.empty()) os << "_" << p.cb_store;
+    if (p.fp == 4 && packed_f32()) os << "_x2";
     std::string s = os.str();
     for (auto &c : s) {
         if (c == '-') c = 'n';
@@ -933,6 +940,7 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     const char *real = p.fp == 4 ? "float" : "double";
     const char *vec = p.fp == 4 ? "float2" : "double2";
     os << "// generated by bbfft-cuda planner -- do not edit\n";
+    if (p.fp == 4 && packed_f32()) os << "#define BBK_F32X2 1\n";
     os << "#include \"bbfft_kernels.cuh\"\n";
     // every stub lives in its own namespace so that several can share a translation unit
     os << "namespace stub_" << identifier << " {\n";
@@ -1127,10 +1135,11 @@ long tile_layout_score(tile_params const &p, int padk) {
                             int lo = int(id % q->S);
                             long r = id / q->S;
                             int u = int(r % NSUB), hi = int(r / NSUB);
-                            int base = lo + q->S * ((u / NS1) * NS + u % NS1) + q->S * q->N * hi;
+                            const int pitch = q->pitch ? q->pitch : q->S * q->N;
+                            int base = lo + q->S * ((u / NS1) * NS + u % NS1) + pitch * hi;
                             inpl[l] = tile_phys(base + q->S * NS1 * j, padk);
                             if (last) {
-                                int b2 = lo + q->S * pass_bin_of_sub(*q, u) + q->S * q->N * hi;
+                                int b2 = lo + q->S * pass_bin_of_sub(*q, u) + pitch * hi;
                                 sorted[l] = tile_phys(b2 + q->S * (q->N / R) * j, padk);
                             }
                         }
@@ -1162,6 +1171,14 @@ int tile_cluster_limit() {
 
 bool tile_fusable(problem_2d const &prob, device_props const &dev, int max_cluster) {
     if (prob.N1 < 2 || prob.N2 < 2) return false;
+    if (prob.real != 0) {
+        // one CTA per spectrum tile; the half-length trick needs an even real length
+        if (prob.N1 % 2 != 0 || prob.N1 < 4) return false;
+        const std::uint64_t tile = prob.M * (prob.N1 / 2) * prob.N2; // (columns 0 and N1/2 share a tile column)
+        if (tile < 1024 || tile > (1u << 20)) return false;
+        if (tile_smem_bytes(tile + prob.M * prob.N2, 0, prob.fp) > std::min<std::size_t>(dev.max_smem_per_block, 200 * 1024)) return false;
+        return std::max(max_prime(int(prob.N1 / 2)), max_prime(int(prob.N2))) <= 31;
+    }
     const std::uint64_t tile = prob.M * prob.N1 * prob.N2;
     if (tile < 1024 || tile > (1u << 20)) return false;
     // padding candidates that would not fit are skipped by the layout search; a tile that does not fit one
@@ -1186,10 +1203,19 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     p.M = prob.M;
     p.N1 = prob.N1;
     p.N2 = prob.N2;
-    const std::uint64_t tile = prob.M * prob.N1 * prob.N2;
-    p.tile_stride = prob.tile_stride ? prob.tile_stride : tile;
+    const bool is_real = prob.real != 0;
+    const std::uint64_t NC = prob.N1 / 2 + 1; // spectrum columns of a real tile
+    if (is_real && (prob.N1 % 2 != 0 || prob.N1 < 4)) throw bad_configuration("bbfft-cuda planner: fused real tiles need an even N1");
+    p.real = prob.real;
+    p.spectrum_n1 = NC;
+    // (real tiles: pass A is the half-length complex transform; N1c = its length, the tile holds NC columns)
+    const std::uint64_t N1c = is_real ? prob.N1 / 2 : prob.N1;
+    const std::uint64_t tile = prob.M * N1c * prob.N2; // elements of the shared-memory tile
+    p.tile_stride = prob.tile_stride ? prob.tile_stride : (is_real ? prob.M * NC * prob.N2 : tile);
+    p.real_row = prob.inplace ? 2 * prob.M * NC : prob.M * prob.N1;
+    p.real_tile_stride = p.real_row * prob.N2;
     const int rmax = 16;
-    auto ra = tune.count("RA") ? parse_radices(tune["RA"]) : tile_radices(int(prob.N1), rmax);
+    auto ra = tune.count("RA") ? parse_radices(tune["RA"]) : tile_radices(int(N1c), rmax);
     auto rb = tune.count("RB") ? parse_radices(tune["RB"]) : tile_radices(int(prob.N2), rmax);
     auto fill = [](tile_pass_params &q, std::vector<int> const &r, int N, int S, int O) {
         int prod = 1;
@@ -1218,12 +1244,13 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
             return prob.N1 % c == 0 && prob.N2 % c == 0 && (tile / c) * 2 * std::uint64_t(prob.fp) >= 16 * 1024 &&
                    (prob.M * prob.N1 / c) * 2 * std::uint64_t(prob.fp) >= 128; // >= 128-byte runs in the final store
         };
-        const int limit = chained_req ? 1 : tile_cluster_limit();
+        const int limit = (chained_req || is_real) ? 1 : tile_cluster_limit();
         // the smallest cluster that brings the CTA's share to 32 KiB (or makes the tile fit at all)
         while (cl < limit && (tile / cl) * 2 * std::uint64_t(prob.fp) > 32 * 1024 && ok(cl * 2)) cl *= 2;
         if (tune.count("CL")) {
             int want = std::atoi(tune["CL"].c_str());
-            if (want < 1 || want > 8 || (want & (want - 1)) != 0 || prob.N1 % want != 0 || prob.N2 % want != 0 || (chained_req && want != 1)) {
+            if (want < 1 || want > 8 || (want & (want - 1)) != 0 || prob.N1 % want != 0 || prob.N2 % want != 0 ||
+                ((chained_req || is_real) && want != 1)) {
                 throw bad_configuration("bbfft-cuda planner: bad tile cluster size");
             }
             cl = want;
@@ -1232,8 +1259,8 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     }
     const std::uint64_t local_tile = tile / std::uint64_t(p.cluster);
     // row pass over the CTA's N2 / CL rows; column pass over its N1 / CL columns (S = fastest run M * N1 / CL)
-    fill(p.a, ra, int(prob.N1), int(prob.M), int(prob.N2) / p.cluster);
-    fill(p.b, rb, int(prob.N2), int(prob.M * prob.N1) / p.cluster, 1);
+    fill(p.a, ra, int(N1c), int(prob.M), int(prob.N2) / p.cluster);
+    fill(p.b, rb, int(prob.N2), int(prob.M * N1c) / p.cluster, 1);
 
     // threads: ~16 (fp32) / ~8-16 (fp64) complex elements per thread
     if (tune.count("TH")) {
@@ -1265,13 +1292,21 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     }
     if (tune.count("PADK")) p.PADK = std::atoi(tune["PADK"].c_str());
     p.smem_bytes = tile_smem_bytes(local_tile, p.PADK, p.fp);
+    int scratch_off = 0;
+    if (prob.real == 1) {
+        // r2c: scratch column for the transform of the packed column (bbk::tile_r2c_unpack)
+        scratch_off = int(p.smem_bytes / (2 * std::size_t(p.fp)));
+        p.smem_bytes += std::size_t(prob.M * prob.N2) * 2 * std::size_t(p.fp);
+    }
     if (p.smem_bytes > dev.max_smem_per_block) {
         throw bad_configuration("bbfft-cuda planner: tile does not fit into shared memory");
     }
     // resident CTAs
     {
         int words = (p.fp == 4 ? 2 : 4) * tile_regs_complex(p);
-        int need = words + words / 4 + 32;
+        // (real tiles: 16 elements per thread of a 512-thread CTA compile to 62-64 registers without spilling,
+        // and two resident CTAs measured 0.56 against 0.44 of the HBM peak for 2d r2c fp32 128 x 128)
+        int need = words + words / 4 + (is_real ? 24 : 32);
         int mb = int(std::min<std::size_t>({std::size_t(4), dev.smem_per_sm / (p.smem_bytes + 1024),
                                             std::size_t(2048 / p.threads)}));
         mb = std::max(mb, 1);
@@ -1281,6 +1316,7 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     if (tune.count("MB")) p.min_blocks = std::max(1, std::atoi(tune["MB"].c_str()));
     p.max_regs = reg_cap(p.threads, p.min_blocks);
     p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
+    if (is_real && p.chained) throw bad_configuration("bbfft-cuda planner: fused real tiles are not chained");
     // Persistent grid + asynchronous load of the next tile (bbk::fft2d_tile_persistent): a switch
     // (PS=1 / BBFFT_CUDA_TILE_ASYNC=1), off by default.  Measured on the B200 (profiles/r02e_tile_pdl.txt)
     // it loses a little -- 2d fp32 128x128 at 1 GiB: 517 us against 499 us; 3d fp64 64^3: 204 against
@@ -1290,24 +1326,69 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     p.persistent = false;
     if (char const *e = std::getenv("BBFFT_CUDA_TILE_ASYNC")) p.persistent = !p.chained && *e == '1';
     if (tune.count("PS")) p.persistent = !p.chained && std::atoi(tune["PS"].c_str()) != 0;
-    if (p.cluster > 1) p.persistent = false;
+    if (p.cluster > 1 || is_real) p.persistent = false;
+    // Staged pipeline (bbk::fft2d_tile_staged): SG=<rows> / BBFFT_CUDA_TILE_STAGE=<rows> (-1: as many rows of pass A
+    // as the shared memory beside the tile holds at the planned number of resident CTAs).
+    {
+        // Default: on, with bulk copies, for tiles that run ONE CTA per SM and more than one tile per CTA -- there
+        // nothing else overlaps the loads (2d fp32 128x128 at 1 GiB: 498 -> 483 us, profiles/r02v_tile.log); off
+        // for smaller tiles, whose two to four resident CTAs overlap each other better than one CTA overlaps
+        // itself (fp32 64x64: 0.99 of the HBM peak plain, 0.85 staged).
+        long rows = 0;
+        bool bulk_default = false;
+        if (p.min_blocks == 1 && prob.K >= 2 * std::uint64_t(dev.sm_count)) {
+            rows = -1;
+            bulk_default = true;
+        }
+        if (char const *e = std::getenv("BBFFT_CUDA_TILE_STAGE")) rows = std::atol(e);
+        if (tune.count("SG")) rows = std::atol(tune["SG"].c_str());
+        if (p.chained || p.cluster > 1 || is_real) rows = 0;
+        p.stage = 0;
+        p.stage_off = 0;
+        if (rows != 0) {
+            const std::size_t elem = 2 * std::size_t(p.fp);
+            const std::size_t row = std::size_t(p.a.S) * std::size_t(p.a.N); // elements of one row of pass A
+            const std::size_t off = (p.smem_bytes / elem + 1) / 2 * 2;       // 16-byte aligned for fp32, too
+            const std::size_t budget = std::min<std::size_t>(dev.max_smem_per_block,
+                                                             dev.smem_per_sm / std::size_t(p.min_blocks) - 1024);
+            long fit = budget > off * elem ? long((budget - off * elem) / (row * elem)) : 0;
+            fit = std::min<long>(fit, long(p.a.O));
+            if (rows < 0 || rows > fit) rows = fit;
+            if (row % 2 != 0) rows = rows / 2 * 2;
+            // (16 bytes behind the staging buffer hold the mbarrier of the bulk-copy flavour)
+            while (rows > 0 && (off + std::size_t(rows) * row) * elem + 16 > budget) rows -= (row % 2 != 0) ? 2 : 1;
+            if (rows > 0) {
+                p.stage = int(std::size_t(rows) * row);
+                p.stage_off = int(off);
+                p.smem_bytes = (off + std::size_t(p.stage)) * elem + 16;
+                p.persistent = true;
+                p.bulk = bulk_default;
+                if (char const *e = std::getenv("BBFFT_CUDA_TILE_BULK")) p.bulk = *e == '1';
+                if (tune.count("BK")) p.bulk = std::atoi(tune["BK"].c_str()) != 0;
+            }
+        }
+    }
 
     // identifier
     {
         std::ostringstream os;
-        os << "bbfft_c2c2d" << (p.dir < 0 ? "_m1" : "_p1") << "_f" << (p.fp * 8) << "_M" << p.M << "_N" << p.N1
+        os << (p.real == 1 ? (prob.inplace ? "bbfft_r2c2di" : "bbfft_r2c2d") : p.real == 2 ? (prob.inplace ? "bbfft_c2r2di" : "bbfft_c2r2d") : "bbfft_c2c2d")
+           << (p.dir < 0 ? "_m1" : "_p1") << "_f" << (p.fp * 8) << "_M" << p.M << "_N" << p.N1
            << "x" << p.N2 << "_ra";
         for (int s = 0; s < p.a.L; ++s) os << (s ? "x" : "") << p.a.radix[s];
         os << "_rb";
         for (int s = 0; s < p.b.L; ++s) os << (s ? "x" : "") << p.b.radix[s];
         os << "_th" << p.threads << "_mb" << p.min_blocks << "_pk" << p.PADK << "_ts" << p.tile_stride;
         if (p.chained) os << "_ch";
-        if (p.persistent) os << "_ps";
+        if (p.persistent && !p.stage) os << "_ps";
+        if (p.stage) os << "_sg" << p.stage << (p.bulk ? "b" : "");
         if (p.cluster > 1) os << "_cl" << p.cluster;
+        if (p.fp == 4 && packed_f32()) os << "_x2";
         plan.identifier = os.str();
     }
     // twiddles: pass A stages, then pass B stages (same construction as the 1d table)
     std::vector<int> off_a(4, 0), off_b(4, 0);
+    int tw_real = 0;
     {
         auto add = [&](tile_pass_params const &q, std::vector<int> &off) {
             int NS = q.N;
@@ -1329,6 +1410,16 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         };
         add(p.a, off_a);
         add(p.b, off_b);
+        if (is_real) {
+            // split / merge twiddles of the half-length trick: w_{N1}^{dir i}, i = 0 .. N1/2 (as the 1d real kernels)
+            tw_real = int(plan.twiddle.size() / 2);
+            for (std::uint64_t i = 0; i <= N1c; ++i) {
+                double re, im;
+                unit_root(long(i), long(2 * N1c), p.dir, re, im);
+                plan.twiddle.push_back(re);
+                plan.twiddle.push_back(im);
+            }
+        }
         if (plan.twiddle.empty()) {
             plan.twiddle.push_back(1.0);
             plan.twiddle.push_back(0.0);
@@ -1338,7 +1429,9 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
     {
         std::ostringstream os;
         const char *real = p.fp == 4 ? "float" : "double";
-        os << "// generated by bbfft-cuda planner -- do not edit\n#include \"bbfft_kernels.cuh\"\n";
+        os << "// generated by bbfft-cuda planner -- do not edit\n";
+        if (p.fp == 4 && packed_f32()) os << "#define BBK_F32X2 1\n";
+        os << "#include \"bbfft_kernels.cuh\"\n";
         os << "namespace stub_" << plan.identifier << " {\n";
         std::set<int> rs;
         for (int s = 0; s < p.a.L; ++s) rs.insert(p.a.radix[s]);
@@ -1346,7 +1439,8 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
         for (int r : rs) emit_w_table(os, r);
         auto emit_pass = [&](char const *name, tile_pass_params const &q, std::vector<int> const &off, long gs) {
             os << "struct " << name << " {\n    static constexpr int N = " << q.N << ", S = " << q.S << ", O = " << q.O
-               << ", L = " << q.L << ", GS = " << gs << ";\n";
+               << ", L = " << q.L << ", GS = " << gs << ", PITCH = " << (q.pitch ? q.pitch : q.S * q.N)
+               << ", GPITCH = " << gs * q.N << ";\n";
             os << "    static BBK_CE int radix(int s) {\n        constexpr int r[4] = {" << q.radix[0] << ", "
                << q.radix[1] << ", " << q.radix[2] << ", " << q.radix[3] << "};\n        return r[s];\n    }\n";
             os << "    static BBK_CE int tw_off(int s) {\n        constexpr int r[4] = {" << off[0] << ", " << off[1]
@@ -1359,12 +1453,15 @@ tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev, std::s
             os << "    template <int S_> using WR = typename WRsel<S_>::type;\n};\n";
         };
         emit_pass("PassA", p.a, off_a, long(p.a.S));
-        emit_pass("PassB", p.b, off_b, long(prob.M * prob.N1)); // rows of the whole tile in global memory
+        emit_pass("PassB", p.b, off_b, long(prob.M * (is_real ? NC : prob.N1))); // rows of the whole tile in global memory
         os << "struct C {\n    using real_t = " << real << ";\n    using PA = PassA;\n    using PB = PassB;\n";
         os << "    static constexpr int DIR = " << p.dir << ", THREADS = " << p.threads << ", PADK = " << p.PADK
            << ", CL = " << p.cluster << ", N2L = " << (prob.N2 / std::uint64_t(p.cluster)) << ", ROWLEN = " << (prob.M * prob.N1)
+           << ", STG = " << p.stage << ", STG_OFF = " << p.stage_off << ", BULK = " << (p.bulk ? 1 : 0)
+           << ", REAL = " << p.real << ", TW_REAL = " << tw_real << ", SCR_OFF = " << scratch_off
            << ";\n    static constexpr bool PERSIST = " << (p.persistent ? "true" : "false")
-           << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull;\n";
+           << ";\n    static constexpr bbk::u64 TILE_STRIDE = " << p.tile_stride << "ull, RTS = " << p.real_tile_stride
+           << "ull, RROW = " << p.real_row << "ull;\n";
         if (p.chained) {
             os << "    static BBK_DEV bbk::cx<real_t> ld(const void *in, bbk::u64 off) {\n"
                   "        return bbk::ldcg_cx(reinterpret_cast<const bbk::cx<real_t> *>(in) + off);\n    }\n";

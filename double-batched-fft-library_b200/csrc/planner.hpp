@@ -89,11 +89,16 @@ struct problem_2d {
     int fp = 4, dir = -1;
     std::uint64_t M = 1, N1 = 1, N2 = 1, K = 1; // K = number of tiles
     std::uint64_t tile_stride = 0;              // elements between consecutive tiles (0 = packed)
+    // fused real tiles (bbk::fft2d_tile_real_cta): 0 = c2c, 1 = r2c, 2 = c2r; N1 is the real length (even), the
+    // spectrum tile is M x (N1/2+1) x N2; `inplace` selects the padded real rows of the in-place default layout
+    int real = 0;
+    bool inplace = false;
 };
 
 struct tile_pass_params {
     int N = 1, S = 1, O = 1, L = 1;
     int radix[4] = {1, 1, 1, 1};
+    int pitch = 0; // elements between the O blocks of the pass inside the tile (S * N unless rows are padded)
 };
 
 struct tile_params {
@@ -102,9 +107,17 @@ struct tile_params {
     tile_pass_params a, b; // axis n1, axis n2
     int threads = 256, PADK = 0, min_blocks = 1, max_regs = 255;
     bool persistent = false; // persistent grid with the asynchronous tile pipeline (bbk::fft2d_tile_persistent)
+    int stage = 0;           // leading elements of the NEXT tile prefetched into a staging buffer behind the tile
+                             // (bbk::fft2d_tile_staged; whole rows of pass A; implies the persistent grid)
+    int stage_off = 0;       // first element of the staging buffer in shared memory
+    bool bulk = false;       // staging buffer filled by cp.async.bulk + mbarrier (one thread issues) instead of cp.async
     int cluster = 1;         // CTAs per tile (thread-block cluster, bbk::fft2d_tile_cluster); 1 = one CTA owns the tile
     std::size_t smem_bytes = 0;
     bool chained = false; // see kernel_params::chained
+    int real = 0;                          // problem_2d::real
+    std::uint64_t real_tile_stride = 0;    // reals between consecutive real tiles
+    std::uint64_t real_row = 0;            // reals between consecutive real rows (n2) of a tile
+    std::uint64_t spectrum_n1 = 0;         // N1/2 + 1
 };
 
 struct tile_plan {
@@ -119,7 +132,7 @@ struct tile_plan {
 int tile_cluster_limit();
 // (max_cluster = 1: the tile must fit one CTA)
 bool tile_fusable(problem_2d const &prob, device_props const &dev, int max_cluster = 1);
-// Tuning overrides: RA=8x16, RB=16x8, TH=<threads>, PADK, MB.
+// Tuning overrides: RA=8x16, RB=16x8, TH=<threads>, PADK, MB, PS, CL, SG=<rows of pass A staged ahead, -1 = as many as fit>, BK=<0|1> bulk copies.
 tile_plan plan_kernel_2d(problem_2d const &prob, device_props const &dev,
                          std::string const &tune = std::string());
 

@@ -55,8 +55,9 @@ def _compile(desc):
     return C.CDLL(so)
 
 
-def run(cfg, inp, out=None, tune=""):
-    """Execute the planned kernel for a 1d (or fused 2d) `cfg` on numpy buffers (out=None -> in place)."""
+def run(cfg, inp, out=None, tune="", grid=None):
+    """Execute the planned kernel for a 1d (or fused 2d) `cfg` on numpy buffers (out=None -> in place).
+    `grid`: number of CTAs to launch instead of the planned grid (persistent tile kernels walk the tiles)."""
     if cfg.dim == 2 and "CL=" not in tune:
         # thread-block clusters (tiles split over several CTAs, distributed shared memory) are exercised on
         # the GPU tier only: the emulator runs one CTA at a time
@@ -71,7 +72,7 @@ def run(cfg, inp, out=None, tune=""):
     nk = cfg.shape[2] if cfg.dim == 1 else desc["grid"]
     a = Args(inp.ctypes.data, out.ctypes.data, tw.ctypes.data, nk, cfg.shape[0], cfg.istride[1],
              cfg.istride[2], cfg.ostride[1], cfg.ostride[2])
-    rc = lib.emu_launch(C.byref(a), desc["grid"], desc["threads"], desc["smem_bytes"])
+    rc = lib.emu_launch(C.byref(a), grid or desc["grid"], desc["threads"], desc["smem_bytes"])
     if rc != 0:
         raise RuntimeError("emulated kernel failed (rc=%d): %s" % (rc, {2: "divergent barriers", 4: "shared-memory race (see stderr)"}.get(rc, "device-side failure")))
     return out, desc

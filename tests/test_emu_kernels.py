@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emu
-from common import TOL, random_complex, rel_l2
+from common import TOL, cdtype, random_complex, rdtype, rel_l2
 
 
 def _run_c2c(pkg, oracle, M, N, K, fp, d, inplace=False, tune="", istride=None, ostride=None):
@@ -200,6 +200,80 @@ def test_c2c_2d_emulated_tile_kernel_vs_oracle(pkg, oracle, fp, M, N1, N2, K, tu
     z = x.copy()
     emu.run(cfg, z, None, tune)
     assert np.array_equal(z, y)
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("M,N1,N2,K,tune,grid", [
+    (1, 32, 32, 5, "SG=24", 2), (1, 32, 32, 5, "SG=-1", 2), (1, 64, 64, 3, "SG=48", 1), (1, 40, 30, 4, "SG=7", 3),
+    (16, 8, 8, 3, "SG=2", 2), (3, 20, 18, 3, "SG=10", 1), (1, 16, 128, 2, "RA=16,RB=2x8x8,SG=100", 1),
+    (1, 128, 16, 3, "SG=1,PS=1", 2), (1, 32, 32, 4, "PS=1", 3), (2, 25, 49, 2, "TH=128,SG=48", 1),
+    (1, 32, 32, 5, "SG=-1,BK=1", 2), (1, 40, 30, 4, "SG=7,BK=1", 3),
+])
+def test_c2c_2d_emulated_staged_tile_kernel(pkg, oracle, fp, M, N1, N2, K, tune, grid):
+    """The persistent tile kernels (asynchronous pipeline, PS=1; staging buffer for the leading rows of the
+    next tile, SG=<rows>): a CTA walks several tiles, the first stage of pass A reads part of its input from
+    the staging buffer -- bit-identical to the one-tile-per-CTA kernel, and right against the oracle."""
+    rng = np.random.default_rng(M * 1000 + N1 * 7 + N2 * 3 + K + 11)
+    d = -1 if (N1 + N2) % 3 else 1
+    cfg = pkg.make_config(2, [M, N1, N2, K], fp, d, pkg.C2C, inplace=False)
+    ocfg = oracle.make_config(2, [M, N1, N2, K], fp, d, 0, inplace=False)
+    n = M * N1 * N2 * K
+    x = random_complex(rng, (n,), fp)
+    ref = np.zeros(n, dtype=x.dtype)
+    oracle.dft(ocfg, x, ref)
+    plain = np.zeros(n, dtype=x.dtype)
+    base_tune = ",".join(t for t in tune.split(",") if not t.startswith(("SG=", "PS=", "BK=")))
+    emu.run(cfg, x, plain, base_tune)
+    y = np.zeros(n, dtype=x.dtype)
+    _, desc = emu.run(cfg, x, y, tune, grid=grid)
+    assert "_sg" in desc["identifier"] or "_ps" in desc["identifier"]
+    assert rel_l2(y, ref) < TOL[fp] * 0.1
+    assert np.array_equal(y, plain)
+    z = x.copy()
+    emu.run(cfg, z, None, tune, grid=grid)
+    assert np.array_equal(z, y)
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("inplace", [False, True])
+@pytest.mark.parametrize("M,N1,N2,K", [(1, 64, 32, 2), (1, 32, 64, 1), (3, 20, 36, 2), (2, 12, 160, 1), (16, 8, 16, 2),
+                                       (1, 128, 16, 1), (1, 40, 60, 2), (1, 6, 400, 1), (1, 4, 512, 1)])
+def test_real_2d_emulated_fused_tile_kernel(pkg, fp, inplace, M, N1, N2, K):
+    """The fused real tile kernels (bbk::fft2d_tile_real_cta): r2c = half-length pass along n1 from the real rows,
+    split on the pairs (i, N1/2 - i), column pass; c2r = the mirror image.  Against numpy's rfft2 / irfft2 in
+    float64, out of place and in the padded in-place layout."""
+    rng = np.random.default_rng(M * 100 + N1 * 7 + N2 + K)
+    ns = N1 // 2 + 1
+    n1r = 2 * ns if inplace else N1
+    x = rng.uniform(-1, 1, (K, N2, N1, M)).astype(rdtype(fp))
+    ref = np.fft.fft(np.fft.rfft(x.astype(np.float64), axis=2), axis=1)
+    # ---- r2c
+    cfg = pkg.make_config(2, [M, N1, N2, K], fp, pkg.FORWARD, pkg.R2C, inplace=inplace)
+    xin = np.zeros((K, N2, n1r, M), dtype=rdtype(fp))
+    xin[:, :, :N1, :] = x
+    if inplace:
+        buf = xin.reshape(-1).copy()
+        _, desc = emu.run(cfg, buf, None)
+        spec = buf.view(cdtype(fp)).reshape(K, N2, ns, M)
+    else:
+        spec = np.zeros((K, N2, ns, M), dtype=cdtype(fp))
+        _, desc = emu.run(cfg, xin.reshape(-1), spec.reshape(-1))
+    assert desc["identifier"].startswith("bbfft_r2c2d")
+    assert rel_l2(spec, ref) < TOL[fp] * 0.1
+    # ---- c2r from the exact spectrum, imaginary part of X[0] polluted (reference test/r2c.cpp:310-324)
+    cfg = pkg.make_config(2, [M, N1, N2, K], fp, pkg.BACKWARD, pkg.C2R, inplace=inplace)
+    sp = ref.astype(cdtype(fp))
+    want = x.astype(np.float64) * (N1 * N2)
+    if inplace:
+        buf = np.zeros(K * N2 * n1r * M, dtype=rdtype(fp))
+        buf.view(cdtype(fp))[:] = sp.reshape(-1)
+        _, desc = emu.run(cfg, buf, None)
+        back = buf.reshape(K, N2, n1r, M)[:, :, :N1, :]
+    else:
+        back = np.zeros((K, N2, N1, M), dtype=rdtype(fp))
+        _, desc = emu.run(cfg, sp.reshape(-1).copy(), back.reshape(-1))
+    assert desc["identifier"].startswith("bbfft_c2r2d")
+    assert rel_l2(back, want) < TOL[fp] * 0.1
 
 
 # ---- chained nd kernel (bbk::chain): all steps of a 2d/3d plan in one persistent launch ----------

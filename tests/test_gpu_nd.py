@@ -189,8 +189,10 @@ def test_nd_chain_matches_one_launch_per_step(pkg, monkeypatch, fp, ttype, Ns, K
         ref = xr * np.prod(Ns)
         nout, odt, d = ref.size, rdtype(fp), pkg.BACKWARD
     outs = {}
-    for name, env in (("chain", {"BBFFT_CUDA_ND_CHAIN": "1"}), ("steps", {})):
+    # (real transforms: one launch per mode on both sides -- the fused real tile kernel is a different factorization)
+    for name, env in (("chain", {"BBFFT_CUDA_ND_CHAIN": "1"}), ("steps", {"BBFFT_CUDA_ND_FUSE_REAL": "0"})):
         monkeypatch.delenv("BBFFT_CUDA_ND_CHAIN", raising=False)
+        monkeypatch.delenv("BBFFT_CUDA_ND_FUSE_REAL", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         cfg = pkg.make_config(dim, [1] + list(Ns) + [K], fp, d, ttype, inplace=False)
@@ -281,3 +283,153 @@ def test_c2c_nd_tile_split_over_a_cluster(pkg, monkeypatch, fp, cl, M, Ns, K):
         for (y, names), (y0, _) in zip(outs["cluster"], outs["plain"]):
             if "_cl" in names[0]:
                 assert np.array_equal(y, y0), names
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("env", [{"BBFFT_CUDA_TILE_STAGE": "-1"}, {"BBFFT_CUDA_TILE_STAGE": "8", "BBFFT_CUDA_TILE_BULK": "0"},
+                                 {"BBFFT_CUDA_TILE_STAGE": "-1", "BBFFT_CUDA_TILE_BULK": "1"},
+                                 {"BBFFT_CUDA_TILE_ASYNC": "1", "BBFFT_CUDA_TILE_STAGE": "0"}])
+@pytest.mark.parametrize("M,Ns,K", [(1, (128, 128), 700), (1, (64, 64), 1500), (4, (64, 64), 5), (1, (40, 30), 1000), (1, (64, 64, 64), 3)])
+def test_c2c_nd_persistent_tile_pipelines(pkg, monkeypatch, fp, env, M, Ns, K):
+    """The persistent tile kernels: BBFFT_CUDA_TILE_STAGE=<rows> (bbk::fft2d_tile_staged: the leading rows of the
+    next tile wait in a staging buffer beside the tile) and BBFFT_CUDA_TILE_ASYNC=1 (bbk::fft2d_tile_persistent).
+    K is large enough that every CTA of the resident grid walks several tiles.  Forward out of place and
+    backward in place against numpy, bit-identical to the one-tile-per-CTA kernel, and the same twice."""
+    dim = len(Ns)
+    rng = np.random.default_rng(sum(Ns) + M + K)
+    shape_np = (K,) + tuple(reversed(Ns)) + (M,)
+    x = (rng.standard_normal(shape_np) + 1j * rng.standard_normal(shape_np)).astype(cdtype(fp))
+    outs = {}
+    for mode in ("pipe", "plain"):
+        for k in ("BBFFT_CUDA_TILE_STAGE", "BBFFT_CUDA_TILE_ASYNC", "BBFFT_CUDA_TILE_BULK"):
+            monkeypatch.delenv(k, raising=False)
+        if mode == "pipe":
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+        else:
+            monkeypatch.setenv("BBFFT_CUDA_TILE_STAGE", "0")  # (staging is the default for one-CTA-per-SM tiles)
+        res = []
+        for d, inplace in ((pkg.FORWARD, False), (pkg.BACKWARD, True)):
+            cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, d, pkg.C2C, inplace=inplace)
+            plan = pkg.Plan(cfg, stream=_stream())
+            xd = torch.from_numpy(x).cuda()
+            if inplace:
+                plan.execute(xd)
+                yd = xd
+            else:
+                yd = torch.empty_like(xd)
+                plan.execute(xd, yd)
+                y1 = yd.clone()
+                yd.zero_()
+                plan.execute(xd, yd)
+                assert torch.equal(y1, yd), plan.kernel_names
+            torch.cuda.synchronize()
+            res.append((yd.cpu().numpy(), plan.kernel_names))
+            plan.close()
+        outs[mode] = res
+    tag = "_sg" if "BBFFT_CUDA_TILE_STAGE" in env else "_ps"
+    if outs["plain"][0][1][0].startswith("bbfft_c2c2d"):  # (tiles beyond one CTA's shared memory run one pass per mode)
+        assert tag in outs["pipe"][0][1][0], outs["pipe"][0][1]
+    assert tag not in outs["plain"][0][1][0]
+    x64 = x[: min(K, 3)].astype(np.complex128)
+    refs = [np.fft.fftn(x64, axes=_axes(dim)), np.fft.ifftn(x64, axes=_axes(dim)) * np.prod(Ns)]
+    for (y, names), (y0, _), ref in zip(outs["pipe"], outs["plain"], refs):
+        assert rel_l2(y[: min(K, 3)], ref) < TOL[fp], names
+        assert np.array_equal(y, y0), names
+
+
+@pytest.mark.parametrize("fp", [4, 8])
+@pytest.mark.parametrize("inplace", [False, True])
+@pytest.mark.parametrize("M,Ns,K", [(1, (128, 128), 40), (1, (64, 64), 300), (3, (20, 36), 50), (2, (12, 160), 33), (16, (8, 16), 20),
+                                    (1, (128, 16), 9), (1, (40, 60), 64), (1, (256, 64), 7), (1, (64, 64, 8), 5), (1, (32, 32, 32), 4),
+                                    (4, (16, 32, 3), 6)])
+def test_real_nd_fused_tiles(pkg, monkeypatch, fp, inplace, M, Ns, K):
+    """Fused real tile kernels (bbk::fft2d_tile_real_cta: modes 1 and 2 of an r2c / c2r transform in one launch,
+    reference src/common/algorithm/nd_fft.hpp:66-152 runs one launch per mode): against numpy's float64 rfftn /
+    irfftn, against the one-launch-per-mode plan (BBFFT_CUDA_ND_FUSE_REAL=0), the same bits on a second execute,
+    and -- out of place, M = 1 -- with a real tensor that is not aligned to a complex number (falls back)."""
+    dim = len(Ns)
+    N1 = Ns[0]
+    n1s = N1 // 2 + 1
+    n1r = 2 * n1s if inplace else N1
+    rng = np.random.default_rng(sum(Ns) + M + K + 3)
+    x = rng.uniform(-1, 1, (K,) + tuple(reversed(Ns)) + (M,)).astype(rdtype(fp))
+    axes = tuple(range(1, dim + 1))
+    ref = np.fft.rfftn(x.astype(np.float64), axes=axes)
+    spec_shape = (K,) + tuple(reversed(Ns[1:])) + (n1s, M)
+    rt = torch.float32 if fp == 4 else torch.float64
+    ct = torch.complex64 if fp == 4 else torch.complex128
+    xin = np.zeros((K,) + tuple(reversed(Ns[1:])) + (n1r, M), dtype=rdtype(fp))
+    xin[..., :N1, :] = x
+    sp = np.ascontiguousarray(ref.astype(cdtype(fp)))
+    sp.reshape(K, -1)[:, 0] += 0.37j  # the imaginary part of X[0] must be ignored (reference test/r2c.cpp:310-324)
+    got = {}
+    # (the one-launch-per-mode twin compiles four more kernels per case: fp32 out of place only)
+    modes = ("fused", "unfused") if (fp == 4 and not inplace) else ("fused",)
+    for mode in modes:
+        monkeypatch.delenv("BBFFT_CUDA_ND_FUSE_REAL", raising=False)
+        if mode == "unfused":
+            monkeypatch.setenv("BBFFT_CUDA_ND_FUSE_REAL", "0")
+        # ---- r2c
+        cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, pkg.FORWARD, pkg.R2C, inplace=inplace)
+        plan = pkg.Plan(cfg, stream=_stream())
+        names_f = plan.kernel_names
+        if inplace:
+            buf = torch.from_numpy(xin).cuda()
+            plan.execute(buf)
+            torch.cuda.synchronize()
+            spec = buf.cpu().numpy().reshape(-1).view(cdtype(fp)).reshape(spec_shape)
+            buf2 = torch.from_numpy(xin).cuda()
+            plan.execute(buf2)
+            assert torch.equal(buf, buf2)
+        else:
+            xd = torch.from_numpy(xin).cuda()
+            yd = torch.zeros(spec_shape, dtype=ct, device="cuda")
+            plan.execute(xd, yd)
+            y1 = yd.clone()
+            yd.zero_()
+            plan.execute(xd, yd)
+            assert torch.equal(y1, yd)
+            spec = yd.cpu().numpy()
+            if M == 1 and mode == "fused":
+                big = torch.zeros(xin.size + 1, dtype=rt, device="cuda")
+                big[1:] = xd.reshape(-1)
+                yd.zero_()
+                plan.execute(big[1:], yd)  # odd element offset
+                assert rel_l2(yd.cpu().numpy(), ref) < TOL[fp]
+        assert rel_l2(spec, ref) < TOL[fp], names_f
+        plan.close()
+        # ---- c2r
+        cfg = pkg.make_config(dim, [M] + list(Ns) + [K], fp, pkg.BACKWARD, pkg.C2R, inplace=inplace)
+        plan = pkg.Plan(cfg, stream=_stream())
+        names_b = plan.kernel_names
+        if inplace:
+            raw = np.zeros(xin.nbytes, dtype=np.uint8)
+            raw[: sp.nbytes] = sp.view(np.uint8).reshape(-1)
+            buf = torch.from_numpy(raw).cuda()
+            plan.execute(buf)
+            torch.cuda.synchronize()
+            back = buf.cpu().numpy().reshape(-1).view(rdtype(fp)).reshape(xin.shape)[..., :N1, :]
+        else:
+            sd = torch.from_numpy(sp).cuda()
+            od = torch.zeros(x.shape, dtype=rt, device="cuda")
+            plan.execute(sd, od)
+            o1 = od.clone()
+            od.zero_()
+            plan.execute(sd, od)
+            assert torch.equal(o1, od)
+            assert torch.equal(sd, torch.from_numpy(sp).cuda()), "out-of-place c2r must not touch its input"
+            back = od.cpu().numpy()
+            if M == 1 and mode == "fused":
+                big = torch.zeros(x.size + 1, dtype=rt, device="cuda")
+                plan.execute(sd, big[1:])
+                assert rel_l2(big[1:].cpu().numpy().reshape(x.shape), x.astype(np.float64) * np.prod(Ns)) < TOL[fp]
+        assert rel_l2(back, x.astype(np.float64) * np.prod(Ns)) < TOL[fp], names_b
+        plan.close()
+        got[mode] = (spec.copy(), np.array(back, copy=True), names_f, names_b)
+    assert any(n.startswith("bbfft_r2c2d") for n in got["fused"][2]), got["fused"][2]
+    assert any(n.startswith("bbfft_c2r2d") for n in got["fused"][3]), got["fused"][3]
+    if "unfused" in got:
+        assert not any("2d" in n for n in got["unfused"][2] + got["unfused"][3])
+        assert rel_l2(got["fused"][0], got["unfused"][0]) < TOL[fp]
+        assert rel_l2(got["fused"][1], got["unfused"][1]) < TOL[fp]
