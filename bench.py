@@ -329,6 +329,15 @@ def other_configs(peak):
                     env={"BBFFT_CUDA_ND_FUSE": "0"})
         bc.bench_nd(rows, "C4 2d c2c f32 128^2 K=64 (L2 resident)", 4, (128, 128), 64, stream)
         bc.bench_nd(rows, "C4 2d shape at 1 GiB", 4, (128, 128), 8192, stream)
+        # real nd transforms: modes 1 and 2 fused in one tile kernel, against one launch per mode (the reference's
+        # nd_fft decomposition)
+        for ttype, nm in ((bc.pkg.R2C, "r2c"), (bc.pkg.C2R, "c2r")):
+            bc.bench_nd_real(rows, "nd real: 2d %s f32 128^2 K=8192, fused tile" % nm, 4, (128, 128), 8192, stream, ttype)
+            bc.bench_nd_real(rows, "nd real: 2d %s f32 128^2 K=8192, one launch per mode" % nm, 4, (128, 128), 8192, stream,
+                             ttype, env={"BBFFT_CUDA_ND_FUSE_REAL": "0"})
+            bc.bench_nd_real(rows, "nd real: 3d %s f64 64^3 K=64, fused tile + 1d pass" % nm, 8, (64, 64, 64), 64, stream, ttype)
+            bc.bench_nd_real(rows, "nd real: 3d %s f64 64^3 K=64, one launch per mode" % nm, 8, (64, 64, 64), 64, stream, ttype,
+                             env={"BBFFT_CUDA_ND_FUSE_REAL": "0"})
         bc.bench_c2c_1d(rows, "C5 c2c f32 M=16 N=256 identity load/store callbacks", 4, 16, 256, (1 << 30) // (16 * 256 * 8),
                         stream, callbacks=(bc.IDENTITY_CB % dict(v="float2"), "load", "store", "cuda"))
         try:  # last, and optional: a failed stream capture must not cost the rows above

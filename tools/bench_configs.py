@@ -215,6 +215,52 @@ def bench_nd(rows, name, fp, dims, K, stream, tune="", env=None):
     plan.close()
 
 
+def bench_nd_real(rows, name, fp, dims, K, stream, ttype, env=None):
+    """r2c / c2r 2d / 3d, M = 1, out of place; algorithmic bytes = real tensor + spectrum tensor
+    (SURVEY 8d generalised: N reals in, (N1/2+1) N2 .. complex out); cuFFT = torch.fft.rfftn / irfftn."""
+    fwd = ttype == pkg.R2C
+    cfg = pkg.make_config(len(dims), [1] + list(dims) + [K], fp, pkg.FORWARD if fwd else pkg.BACKWARD, ttype, inplace=False)
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        plan = pkg.Plan(cfg, stream=stream)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    tdims = [K] + list(reversed(dims))
+    axes = tuple(range(1, len(dims) + 1))
+    x = torch.rand(*tdims, dtype=rdt(fp), device="cuda")
+    kc = min(K, 4)
+    n = 1
+    for d in dims:
+        n *= d
+    nspec = (dims[0] // 2 + 1) * (n // dims[0])
+    if fwd:
+        y = torch.empty(tdims[:-1] + [dims[0] // 2 + 1], dtype=cdt(fp), device="cuda")
+        plan.execute(x, y)
+        torch.cuda.synchronize()
+        err = rel_l2(y[:kc], torch.fft.rfftn(x[:kc].to(torch.float64), dim=axes))
+        fn = lambda: plan.execute(x, y)
+        cf = lambda: torch.fft.rfftn(x, dim=axes)
+    else:
+        spec = torch.fft.rfftn(x, dim=axes).contiguous()
+        y = torch.empty_like(x)
+        plan.execute(spec, y)
+        torch.cuda.synchronize()
+        err = rel_l2(y[:kc], torch.fft.irfftn(spec[:kc].to(torch.complex128), s=tdims[1:], dim=axes) * n)
+        fn = lambda: plan.execute(spec, y)
+        cf = lambda: torch.fft.irfftn(spec, s=tdims[1:], dim=axes)
+    nbytes = float(n * fp + nspec * 2 * fp) * K
+    flops = 2.5 * n * math.log2(n) * K
+    tb, tm = time_fn(fn, inner=2)
+    tc, _ = time_fn(cf, inner=2)
+    report(rows, name, fp, [1] + list(dims) + [K], nbytes, flops, tb, tm, tc, err, plan.kernel_names)
+    plan.close()
+
+
 IDENTITY_CB = """
 __device__ %(v)s load(%(v)s const* in, size_t offset) { return in[offset]; }
 __device__ void store(%(v)s* out, size_t offset, %(v)s value) { out[offset] = value; }

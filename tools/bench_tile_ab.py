@@ -212,6 +212,12 @@ def main():
             ab_real("3d %s f64 64^3 K=64" % tt, (64, 64, 64), 64, 8, tt, [("one launch per mode", "", unf), ("fused", "", None)], a.rounds)
             ab_real("3d %s f32 128x128x32 K=64" % tt, (128, 128, 32), 64, 4, tt, [("one launch per mode", "", unf), ("fused", "", None)], a.rounds)
         return
+    if a.which == "prof2":
+        # one execute round of the shipped 128 x 128 fp32 tile kernels (c2c staged, r2c / c2r fused), for ncu
+        ab("2d c2c f32 128x128 K=8192", (128, 128), 8192, 4, [("default", "", None)], 1)
+        ab_real("2d r2c f32 128x128 K=8192", (128, 128), 8192, 4, "r2c", [("fused", "", None)], 1)
+        ab_real("2d c2r f32 128x128 K=8192", (128, 128), 8192, 4, "c2r", [("fused", "", None)], 1)
+        return
     if a.which == "prof":
         # three executes of each variant, for ncu
         x2 = {"BBFFT_CUDA_F32X2": "1"}
@@ -226,7 +232,7 @@ def main():
         return
     sg = lambda rows: {"BBFFT_CUDA_TILE_STAGE": str(rows)}
     ab("2d c2c f32 128x128 K=8192", (128, 128), 8192, 4, [
-        ("plain", "", None), ("PS=1", "PS=1", None), ("SG=-1", "SG=-1", None), ("SG=64", "SG=64", None),
+        ("plain", "SG=0", None), ("default", "", None), ("PS=1", "PS=1,SG=0", None), ("SG=-1", "SG=-1", None), ("SG=64", "SG=64", None),
         ("SG=32", "SG=32", None), ("SG=-1,PADK=64", "SG=-1,PADK=64", None), ("SG=-1,TH=512", "SG=-1,TH=512", None),
         ("SG=-1,TH=512,RA=16x8,RB=16x8", "SG=-1,TH=512,RA=16x8,RB=16x8", None),
         ("TH=512", "TH=512", None), ("SG=-1,BK=1", "SG=-1,BK=1", None), ("SG=64,BK=1", "SG=64,BK=1", None),
@@ -240,8 +246,8 @@ def main():
         ("plain", "", None), ("SG=-1", "SG=-1", None), ("SG=-1,MB=2", "SG=-1,MB=2", None), ("SG=-1,MB=3", "SG=-1,MB=3", None),
         ("SG=-1,MB=3,BK=1", "SG=-1,MB=3,BK=1", None),
     ], a.rounds)
-    ab("2d c2c f64 128x64 K=8192", (128, 64), 8192, 8, [("plain", "", None), ("SG=-1", "SG=-1", None)], a.rounds)
-    ab("2d c2c f32 256x64 K=8192", (256, 64), 8192, 4, [("plain", "", None), ("SG=-1", "SG=-1", None)], a.rounds)
+    ab("2d c2c f64 128x64 K=8192", (128, 64), 8192, 8, [("plain", "SG=0", None), ("default", "", None), ("SG=-1,BK=0", "SG=-1,BK=0", None)], a.rounds)
+    ab("2d c2c f32 256x64 K=8192", (256, 64), 8192, 4, [("plain", "SG=0", None), ("default", "", None), ("SG=-1,BK=0", "SG=-1,BK=0", None)], a.rounds)
     ab("3d c2c f64 64^3 K=64", (64, 64, 64), 64, 8, [
         ("plain", "", None), ("STAGE=-1", "", sg(-1)), ("STAGE=32", "", sg(32)), ("STAGE=16", "", sg(16)),
         ("STAGE=-1,BULK", "", dict(sg(-1), BBFFT_CUDA_TILE_BULK="1")),
