@@ -46,7 +46,9 @@ BUILTIN_DESCRIPTORS = (
 # both repetitions by more than 2 %, and the entries of csrc/wisdom.inc that were chosen from NVRTC-built
 # candidates inside the sweep (tools/bench_ab.py).  Arithmetic is unaffected: every multiply is an explicit-
 # rounding intrinsic, a GPU test pins nvcc == NVRTC bit for bit.
-NVRTC_BUILT = {4: (2, 147, 150, 384),
+# fp32 sizes planned with packed adds (X2=1 in csrc/wisdom.inc, profiles/r02y_x2sweep.log) define BBK_F32X2 for their
+# translation unit, so they must be alone in it: 196 ... 490 below.
+NVRTC_BUILT = {4: (2, 147, 150, 384, 196, 245, 270, 315, 324, 343, 350, 392, 405, 490),
                8: (54, 90, 96, 100, 112, 120, 128, 160, 175, 243, 245, 250, 294, 315, 343, 392, 405, 448, 490)}
 
 

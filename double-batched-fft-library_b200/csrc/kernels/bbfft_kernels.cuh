@@ -1614,7 +1614,14 @@ BBK_DEV void tile_stage(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, u64 
                         // c2r tile, column pass: the tile holds N1/2 columns; column 0 carries the spectrum columns
                         // 0 and N1/2 -- both transform to REAL columns -- as one complex column X0 + i XH
                         if (lo < C::PA::S) {
-                            const cx<T> xh = C::ld(a.in, gbase + u64(lo + C::PA::S * C::PA::N + P::GS * (pos0 + NS1 * j)));
+                            cx<T> xh = C::ld(a.in, gbase + u64(lo + C::PA::S * C::PA::N + P::GS * (pos0 + NS1 * j)));
+                            // the four entries (0 | N1/2, 0 | N2/2) of a real signal's spectrum are real: their
+                            // imaginary parts are ignored, like the 1d c2r ignores imag X[0] (reference
+                            // test/r2c.cpp:310-324: "match the behaviour of other FFT libraries")
+                            if (pos0 + NS1 * j == 0 || 2 * (pos0 + NS1 * j) == P::N) {
+                                v[i][j].y = T(0);
+                                xh.y = T(0);
+                            }
                             v[i][j] = cx<T>{v[i][j].x - xh.y, v[i][j].y + xh.x};
                         }
                     }

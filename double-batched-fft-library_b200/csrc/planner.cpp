@@ -16,6 +16,7 @@
 namespace bbfft::cuda {
 
 static void unit_root(long num, long den, int dir, double &re, double &im);
+static bool packed_f32();
 static void emit_w_table(std::ostringstream &os, int R);
 
 // ------------------------------------------------------------------------------------------
@@ -740,6 +741,10 @@ kernel_plan plan_kernel_1d(problem_1d const &prob, device_props const &dev,
     p.max_regs = reg_cap(p.threads, p.min_blocks);
 
     p.chained = tune.count("CH") && std::atoi(tune["CH"].c_str()) != 0;
+    // packed fp32 adds: a per-kernel choice (the stub defines BBK_F32X2 for its translation unit; bit-identical
+    // results, 3-5 % faster for the add-heavy 7-point sizes, slower for others: profiles/r02v_x2.log)
+    p.x2 = p.fp == 4 && !p.chained && (packed_f32() || (tune.count("X2") && std::atoi(tune["X2"].c_str()) != 0));
+    if (tune.count("X2") && std::atoi(tune["X2"].c_str()) == 0) p.x2 = false;
     // real in-place transforms need one CTA to own every m of a k slice, like the reference
     // (src/base/generator/small_batch_fft.cpp:38, factor2_slm_fft.cpp:63)
     plan.inplace_unsupported = real && !p.klanes && std::uint64_t(p.ML) < prob.M;
@@ -774,7 +779,7 @@ std::string make_identifier(kernel_params const &p) {
     if (p.chained) os << "_ch";
     if (!p.cb_load.empty()) os << "_" << p.cb_load;
     if (!p.cb_store.empty()) os << "_" << p.cb_store;
-    if (p.fp == 4 && packed_f32()) os << "_x2";
+    if (p.x2) os << "_x2";
     std::string s = os.str();
     for (auto &c : s) {
         if (c == '-') c = 'n';
@@ -940,7 +945,7 @@ std::string emit_stub(kernel_params const &p, std::string const &identifier,
     const char *real = p.fp == 4 ? "float" : "double";
     const char *vec = p.fp == 4 ? "float2" : "double2";
     os << "// generated by bbfft-cuda planner -- do not edit\n";
-    if (p.fp == 4 && packed_f32()) os << "#define BBK_F32X2 1\n";
+    if (p.x2) os << "#define BBK_F32X2 1\n";
     os << "#include \"bbfft_kernels.cuh\"\n";
     // every stub lives in its own namespace so that several can share a translation unit
     os << "namespace stub_" << identifier << " {\n";

@@ -46,6 +46,7 @@ struct kernel_params {
     bool klanes = false, load_staged = false, store_staged = false;
     bool pair_load = false, pair_store = false; // real side is read/written as aligned complex words
     bool real_fused = false; // real pre/post pass fused into the first/last stage (mirrored sub-FFT pairs)
+    bool x2 = false;         // fp32: packed adds (add.f32x2 -> FADD2) in this kernel's translation unit (tune X2=1)
     bool chained = false;    // stub is a step of a chain kernel: no entry point, L2-only (ld.global.cg) loads
     std::uint64_t M = 1;
     std::int64_t is1 = 1, is2 = 1, os1 = 1, os2 = 1;

@@ -263,6 +263,7 @@ def test_real_2d_emulated_fused_tile_kernel(pkg, fp, inplace, M, N1, N2, K):
     # ---- c2r from the exact spectrum, imaginary part of X[0] polluted (reference test/r2c.cpp:310-324)
     cfg = pkg.make_config(2, [M, N1, N2, K], fp, pkg.BACKWARD, pkg.C2R, inplace=inplace)
     sp = ref.astype(cdtype(fp))
+    sp[:, 0, 0, :] += 0.37j  # ignored
     want = x.astype(np.float64) * (N1 * N2)
     if inplace:
         buf = np.zeros(K * N2 * n1r * M, dtype=rdtype(fp))

@@ -327,7 +327,7 @@ def test_c2c_nd_persistent_tile_pipelines(pkg, monkeypatch, fp, env, M, Ns, K):
             res.append((yd.cpu().numpy(), plan.kernel_names))
             plan.close()
         outs[mode] = res
-    tag = "_sg" if "BBFFT_CUDA_TILE_STAGE" in env else "_ps"
+    tag = "_ps" if env.get("BBFFT_CUDA_TILE_ASYNC") == "1" else "_sg"
     if outs["plain"][0][1][0].startswith("bbfft_c2c2d"):  # (tiles beyond one CTA's shared memory run one pass per mode)
         assert tag in outs["pipe"][0][1][0], outs["pipe"][0][1]
     assert tag not in outs["plain"][0][1][0]

@@ -187,6 +187,65 @@ def ab_real(title, dims, K, fp, ttype, variants, rounds):
     sys.stdout.flush()
 
 
+REAL_SWEEP = (2, 3, 4, 7, 8, 15, 16, 27, 32, 49, 64, 100, 105, 128, 135, 200, 243, 256, 315, 343, 384, 400, 441, 480, 500, 512)
+
+
+def x2_sweep(rounds):
+    """Packed fp32 adds per kernel: every fp32 size of the c2c sweep and of the r2c / c2r M=16 sweep, planned with and
+    without X2=1, timed interleaved; prints the ratio (> 1: the packed build is faster)."""
+    aot = importlib.import_module("double-batched-fft-library_b200.aot")
+    jobs = [("c2c", n) for n in aot.smooth_sizes()] + [(t, n) for t in ("r2c", "c2r") for n in REAL_SWEEP if n > 2]
+    if os.environ.get("SHARD"):  # "i/n": every n-th job (parallel warm-up on the build box)
+        i, n_sh = map(int, os.environ["SHARD"].split("/"))
+        jobs = jobs[i::n_sh]
+    for ttype, n in jobs:
+        if ttype == "c2c":
+            K = (1 << 30) // (16 * n * 8)
+            cfg = pkg.make_config(1, [16, n, K], 4, pkg.FORWARD, pkg.C2C, inplace=False)
+        else:
+            K = (1 << 29) // (16 * n * 4)
+            fwd = ttype == "r2c"
+            cfg = pkg.make_config(1, [16, n, K], 4, pkg.FORWARD if fwd else pkg.BACKWARD, pkg.R2C if fwd else pkg.C2R, inplace=False)
+        if WARM:
+            for tune in ("X2=0", "X2=1"):
+                try:
+                    pkg.compile_to_cubin(pkg.describe(cfg, tune)["source"])
+                except Exception as e:
+                    print("warm failed", ttype, n, tune, str(e)[:80])
+            continue
+        if ttype == "c2c":
+            src = torch.view_as_complex(torch.rand(K * n * 16, 2, dtype=torch.float32, device="cuda"))
+            dst = torch.empty_like(src)
+        else:
+            xr = torch.rand(K * n * 16, dtype=torch.float32, device="cuda")
+            xc = torch.view_as_complex(torch.rand(K * (n // 2 + 1) * 16, 2, dtype=torch.float32, device="cuda"))
+            src, dst = (xr, torch.empty_like(xc)) if ttype == "r2c" else (xc, torch.empty_like(xr))
+        plans = [pkg.Plan(cfg, stream=torch.cuda.current_stream().cuda_stream, tune=t) for t in ("X2=0", "X2=1")]
+        outs = []
+        for p in plans:
+            p.execute(src, dst)
+            torch.cuda.synchronize()
+            outs.append(dst.clone())
+        same = bool(torch.equal(outs[0], outs[1]))
+        times = [[], []]
+        for r in range(rounds):
+            for i in ((0, 1) if r % 2 == 0 else (1, 0)):
+                plans[i].execute(src, dst)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    plans[i].execute(src, dst)
+                e1.record()
+                torch.cuda.synchronize()
+                times[i].append(e0.elapsed_time(e1) / 3 * 1e3)
+        t0, t1 = statistics.median(times[0]), statistics.median(times[1])
+        print("%s f32 N=%-4d plain %8.2f us  x2 %8.2f us  ratio %.3f  bit-identical %s" % (ttype, n, t0, t1, t0 / t1, same))
+        sys.stdout.flush()
+        for p in plans:
+            p.close()
+        del src, dst
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=7)
@@ -195,6 +254,8 @@ def main():
     a = ap.parse_args()
     global WARM
     WARM = a.warm
+    if a.which == "x2sweep":
+        return x2_sweep(a.rounds)
     if a.which == "real":
         unf = {"BBFFT_CUDA_ND_FUSE_REAL": "0"}
         for tt in ("r2c", "c2r"):
