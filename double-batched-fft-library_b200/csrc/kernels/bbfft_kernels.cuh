@@ -1896,47 +1896,49 @@ template <class C> BBK_DEV void fft2d_tile_staged(args const &a) {
 template <class C, bool FORWARD_SPLIT> BBK_DEV void tile_real_pairs(args const &a, BBK_SPTR(cx<typename C::real_t>) sm, int tid) {
     using T = typename C::real_t;
     using PA = typename C::PA;
-    constexpr int H = PA::N;           // half length: complex columns of the tile
+    constexpr int H = PA::N;         // half length: complex columns of the tile
     constexpr int M = PA::S;
-    constexpr int UNITS = H / 2 + 1;   // pairs (i, H - i), i = 1 .. H/2, and the packed column 0
+    constexpr int UNITS = H / 2;     // pairs (i, H - i), i = 1 .. H/2 (i = H/2 pairs with itself when H is even)
     constexpr int TOTAL = M * UNITS * PA::O;
     constexpr int CNT = (TOTAL + C::THREADS - 1) / C::THREADS;
     const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
+    // (a power-of-two number of units per row keeps a warp inside one row: the version that walked the H/2+1
+    // units i = 0 .. H/2 of a row wrapped every warp over two rows and paid two-way bank conflicts on every
+    // access, profiles/r02zb_ncu_r2c_tile.txt)
     static_for<0, CNT>([&](auto ii) {
         constexpr int c = decltype(ii)::value;
         const int id = tid + C::THREADS * c;
         if (TOTAL % C::THREADS == 0 || id < TOTAL) {
             const int lo = id % M, r = id / M;
-            const int i = r % UNITS, hi = r / UNITS;
+            const int i = 1 + r % UNITS, hi = r / UNITS;
             const int row = lo + PA::PITCH * hi;
-            const int pi = tile_phys<C>(row + M * i);
-            if (i == 0) {
-                // r2c: y0 = (a, b) -> X[0] = a + b, X[H] = a - b (both real), kept as one complex number;
-                // c2r: (X0, XH) -> z0 = (X0 + XH, X0 - XH): the same map
-                const cx<T> y = sm[pi];
-                sm[pi] = cx<T>{y.x + y.y, y.x - y.y};
+            const int pi = tile_phys<C>(row + M * i), pn = tile_phys<C>(row + M * (H - i));
+            const cx<T> w = ldg_cx(twr + i);
+            const cx<T> iw = cx<T>{-w.y, w.x};
+            const cx<T> yi = sm[pi];
+            const cx<T> yn = sm[pn];
+            if constexpr (FORWARD_SPLIT) {
+                const cx<T> y2 = conj(yn);
+                const cx<T> aa = rmul(y2 + yi, T(0.5));
+                const cx<T> bb = cmul(rmul(y2 - yi, T(0.5)), iw);
+                sm[pi] = aa + bb;
+                if (2 * i != H) sm[pn] = conj(aa - bb);
             } else {
-                const int pn = tile_phys<C>(row + M * (H - i));
-                const cx<T> w = ldg_cx(twr + i);
-                const cx<T> iw = cx<T>{-w.y, w.x};
-                const cx<T> yi = sm[pi];
-                const cx<T> yn = sm[pn];
-                if constexpr (FORWARD_SPLIT) {
-                    const cx<T> y2 = conj(yn);
-                    const cx<T> aa = rmul(y2 + yi, T(0.5));
-                    const cx<T> bb = cmul(rmul(y2 - yi, T(0.5)), iw);
-                    sm[pi] = aa + bb;
-                    if (2 * i != H) sm[pn] = conj(aa - bb);
-                } else {
-                    const cx<T> x2 = conj(yn);
-                    const cx<T> aa = yi + x2;
-                    const cx<T> bb = cmul(yi - x2, iw);
-                    sm[pi] = aa + bb;
-                    if (2 * i != H) sm[pn] = conj(aa - bb);
-                }
+                const cx<T> x2 = conj(yn);
+                const cx<T> aa = yi + x2;
+                const cx<T> bb = cmul(yi - x2, iw);
+                sm[pi] = aa + bb;
+                if (2 * i != H) sm[pn] = conj(aa - bb);
             }
         }
     });
+    // column 0 -- r2c: y0 = (a, b) -> X[0] = a + b, X[H] = a - b (both real), kept as one complex number;
+    // c2r: (X0, XH) -> z0 = (X0 + XH, X0 - XH): the same map
+    for (int id = tid; id < M * PA::O; id += C::THREADS) {
+        const int p0 = tile_phys<C>(id % M + PA::PITCH * (id / M));
+        const cx<T> y = sm[p0];
+        sm[p0] = cx<T>{y.x + y.y, y.x - y.y};
+    }
 }
 
 // r2c: the transform Z of the packed column X0 + i XH sits in the scratch column (natural order); unpack it into

@@ -341,7 +341,7 @@ def test_c2c_nd_persistent_tile_pipelines(pkg, monkeypatch, fp, env, M, Ns, K):
 @pytest.mark.parametrize("fp", [4, 8])
 @pytest.mark.parametrize("inplace", [False, True])
 @pytest.mark.parametrize("M,Ns,K", [(1, (128, 128), 40), (1, (64, 64), 300), (3, (20, 36), 50), (2, (12, 160), 33), (16, (8, 16), 20),
-                                    (1, (128, 16), 9), (1, (40, 60), 64), (1, (256, 64), 7), (1, (64, 64, 8), 5), (1, (32, 32, 32), 4),
+                                    (1, (128, 16), 9), (1, (40, 60), 64), (1, (256, 64), 7), (1, (64, 64, 8), 5), (1, (64, 32, 32), 4),
                                     (4, (16, 32, 3), 6)])
 def test_real_nd_fused_tiles(pkg, monkeypatch, fp, inplace, M, Ns, K):
     """Fused real tile kernels (bbk::fft2d_tile_real_cta: modes 1 and 2 of an r2c / c2r transform in one launch,
