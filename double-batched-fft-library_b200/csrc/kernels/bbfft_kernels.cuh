@@ -1904,7 +1904,10 @@ template <class C, bool FORWARD_SPLIT> BBK_DEV void tile_real_pairs(args const &
     const cx<T> *BBK_RESTRICT twr = reinterpret_cast<const cx<T> *>(a.tw) + C::TW_REAL;
     // (a power-of-two number of units per row keeps a warp inside one row: the version that walked the H/2+1
     // units i = 0 .. H/2 of a row wrapped every warp over two rows and paid two-way bank conflicts on every
-    // access, profiles/r02zb_ncu_r2c_tile.txt)
+    // access, profiles/r02zb_ncu_r2c_tile.txt: 2d r2c fp32 128 x 128 297 -> 264 us.  The accesses to element i
+    // still cross a pad once per half-warp (13 % excess wavefronts, r02zd_ncu_r2c_tile.txt); keeping the group
+    // leaders i = 16 k out of the main loop removes that but costs a second loop and measured slower on
+    // balance, profiles/r02ze_real_tiles_leaderless.log)
     static_for<0, CNT>([&](auto ii) {
         constexpr int c = decltype(ii)::value;
         const int id = tid + C::THREADS * c;
