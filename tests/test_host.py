@@ -215,3 +215,55 @@ def test_tensor_indexer_header(tmp_path):
                            os.path.join(ROOT, "tests", "cpp", "test_tensor_indexer.cpp"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_real_nd_plans_fuse_modes_one_and_two(pkg, monkeypatch):
+    """r2c / c2r 2d with an even N1 whose half-length tile fits shared memory plan as ONE fused real tile kernel
+    (bbk::fft2d_tile_real_cta); odd N1, tiny tiles and BBFFT_CUDA_ND_FUSE_REAL=0 keep one launch per mode."""
+    for fp in (4, 8):
+        for inplace in (False, True):
+            d = pkg.describe(pkg.make_config(2, [1, 128, 64, 9], fp, pkg.FORWARD, pkg.R2C, inplace=inplace))
+            assert d["identifier"].startswith("bbfft_r2c2di_" if inplace else "bbfft_r2c2d_"), d["identifier"]
+            # tile: N1/2 columns x N2 rows, plus the scratch column of the r2c unpack
+            assert d["smem_bytes"] >= (64 * 64 + 64) * 2 * fp and d["smem_bytes"] < 2 * 64 * 64 * 2 * fp
+            assert d["grid"] == 9
+            d = pkg.describe(pkg.make_config(2, [1, 128, 64, 9], fp, pkg.BACKWARD, pkg.C2R, inplace=inplace))
+            assert d["identifier"].startswith("bbfft_c2r2di_" if inplace else "bbfft_c2r2d_"), d["identifier"]
+    for shape in ([1, 127, 64, 3], [1, 8, 8, 3]):  # odd N1; a tile below 1024 elements
+        with pytest.raises(pkg.BadConfiguration):
+            pkg.describe(pkg.make_config(2, shape, 4, pkg.FORWARD, pkg.R2C, inplace=False))
+    monkeypatch.setenv("BBFFT_CUDA_ND_FUSE_REAL", "0")
+    with pytest.raises(pkg.BadConfiguration):
+        pkg.describe(pkg.make_config(2, [1, 128, 64, 9], 4, pkg.FORWARD, pkg.R2C, inplace=False))
+
+
+def test_tile_kernel_variants_are_planner_decisions(pkg, monkeypatch):
+    """The staged persistent tile kernel (staging buffer + bulk copies) is the default exactly for tiles that run one
+    CTA per SM with more than one tile per CTA; SG / PS / BK tune keys and the environment switches override."""
+    big = pkg.make_config(2, [1, 128, 128, 8192], 4, pkg.FORWARD, pkg.C2C, inplace=False)
+    few = pkg.make_config(2, [1, 128, 128, 64], 4, pkg.FORWARD, pkg.C2C, inplace=False)
+    small = pkg.make_config(2, [1, 64, 64, 8192], 4, pkg.FORWARD, pkg.C2C, inplace=False)
+    d = pkg.describe(big)
+    assert "_sg" in d["identifier"] and d["identifier"].endswith("b") and d["smem_bytes"] <= 227 * 1024
+    assert "#include" in d["source"] and "STG = " in d["source"] and "BULK = 1" in d["source"]
+    for cfg, tune in ((few, ""), (small, ""), (big, "SG=0")):
+        ident = pkg.describe(cfg, tune)["identifier"]
+        assert "_sg" not in ident and "_ps" not in ident, ident
+    assert pkg.describe(big, "SG=0,PS=1")["identifier"].endswith("_ps")
+    assert pkg.describe(big, "SG=32,BK=0")["identifier"].endswith("_sg4096")
+    monkeypatch.setenv("BBFFT_CUDA_TILE_STAGE", "0")
+    assert "_sg" not in pkg.describe(big)["identifier"]
+
+
+def test_packed_add_flag_is_per_kernel(pkg, monkeypatch):
+    """X2=1 (csrc/wisdom.inc, profiles/r02y_x2sweep.log): fp32 kernels of the measured sizes define BBK_F32X2 for their
+    translation unit and carry _x2 in the identifier; fp64 and untuned plans never do."""
+    d = pkg.describe(pkg.make_config(1, [16, 343, 64], 4, inplace=False))
+    assert d["identifier"].endswith("_x2") and d["source"].lstrip().splitlines()[1].startswith("#define BBK_F32X2")
+    assert not pkg.describe(pkg.make_config(1, [16, 343, 64], 8, inplace=False))["identifier"].endswith("_x2")
+    assert not pkg.describe(pkg.make_config(1, [16, 512, 64], 4, inplace=False))["identifier"].endswith("_x2")
+    assert not pkg.describe(pkg.make_config(1, [16, 343, 64], 4, inplace=False), "X2=0")["identifier"].endswith("_x2")
+    assert pkg.describe(pkg.make_config(1, [16, 243, 64], 4, pkg.FORWARD, pkg.R2C, inplace=False))["identifier"].endswith("_x2")
+    assert pkg.describe(pkg.make_config(1, [16, 343, 64], 8, inplace=False), "X2=1")["identifier"].endswith("_x2") is False
+    monkeypatch.setenv("BBFFT_CUDA_NO_WISDOM", "1")
+    assert not pkg.describe(pkg.make_config(1, [16, 343, 64], 4, inplace=False))["identifier"].endswith("_x2")
