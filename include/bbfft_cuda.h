@@ -65,8 +65,9 @@ int bbfft_cuda_cache_size(bbfft_cuda_cache_t cache);
  * `stream` is a cudaStream_t (NULL = default stream); device < 0 = current device. */
 int bbfft_cuda_plan_create(bbfft_cuda_plan_t *plan, const bbfft_cuda_config *cfg, void *stream, int device,
                            bbfft_cuda_cache_t cache);
-/* Same, with planner overrides ("R=8x8,T=8,BH=2,..." for 1d plans, "RA=8x8,RB=8x8,TH=256,MB=2,PADK=8"
- * for 2d configurations that run as one fused tile kernel; used by the auto-tuner). */
+/* Same, with planner overrides ("R=8x8,T=8,BH=2,...,X2=1" for 1d plans, "RA=8x8,RB=8x8,TH=256,MB=2,PADK=8,SG=-1,BK=1"
+ * for 2d configurations -- c2c, r2c or c2r -- that run as one fused tile kernel; used by the auto-tuner and the
+ * A/B tools.  X2: packed fp32 adds; SG / BK: staging buffer of the persistent tile kernel and its bulk copies). */
 int bbfft_cuda_plan_create_tuned(bbfft_cuda_plan_t *plan, const bbfft_cuda_config *cfg, void *stream,
                                  int device, bbfft_cuda_cache_t cache, const char *tune);
 /* plan::execute(in, out) (include/bbfft/plan.hpp:77-131): asynchronous, stream ordered;
