@@ -1440,12 +1440,15 @@ BBK_DEV cx<double> ld_cluster(const cx<double> *sm, int idx, unsigned rank) {
 // layout puts every element at its own 8- / 16-byte aligned slot).  The copy engine of the SM moves
 // the data while the issuing warps go on computing; cp.async.wait_group + a CTA barrier publish it.
 #ifdef BBFFT_EMU
-template <class SP, class E> BBK_DEV void async_copy_elem(SP sm, int phys, const E *src) { sm[phys] = *src; }
+// (emulator: the destination is poisoned at the issue and the data lands at the wait, tests/emu/cuda_emu.hpp)
+template <class SP, class E> BBK_DEV void async_copy_elem(SP sm, int phys, const E *src) {
+    ::bbfft_emu::async_issue_raw(::bbfft_emu::raw_ptr(sm) + phys, src, sizeof(E), false);
+}
 template <class SP, class E> BBK_DEV void async_copy_16(SP sm, int phys, const E *src) {
-    for (int i = 0; i < int(16 / sizeof(E)); ++i) sm[phys + i] = src[i];
+    ::bbfft_emu::async_issue_raw(::bbfft_emu::raw_ptr(sm) + phys, src, 16, false);
 }
 BBK_DEV void async_commit() {}
-BBK_DEV void async_wait_all() {}
+BBK_DEV void async_wait_all() { ::bbfft_emu::async_wait_raw(false); }
 #else
 template <class E> BBK_DEV void async_copy_elem(E *sm, int phys, const E *src) {
     const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(sm + phys));
@@ -1472,9 +1475,9 @@ BBK_DEV void async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memor
 template <class SP> BBK_DEV void mbar_init(SP, int) {}
 template <class SP> BBK_DEV void mbar_expect(SP, int, unsigned) {}
 template <class SP, class E> BBK_DEV void bulk_copy(SP sm, int phys, const E *src, unsigned bytes, int) {
-    for (unsigned i = 0; i < bytes / sizeof(E); ++i) sm[phys + int(i)] = src[i];
+    ::bbfft_emu::async_issue_raw(::bbfft_emu::raw_ptr(sm) + phys, src, bytes, true);
 }
-template <class SP> BBK_DEV void mbar_wait(SP, int, unsigned) {}
+template <class SP> BBK_DEV void mbar_wait(SP, int, unsigned) { ::bbfft_emu::async_wait_raw(true); }
 #else
 template <class E> BBK_DEV void mbar_init(E *sm, int bar) {
     const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(sm + bar));

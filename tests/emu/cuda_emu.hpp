@@ -9,11 +9,20 @@
 #define BBFFT_CUDA_EMU_HPP
 #include <stddef.h>
 namespace bbfft_emu {
+// An asynchronous shared-memory copy (cp.async / cp.async.bulk) in flight: the destination is undefined from the
+// issue to the wait that completes it.
+struct pending_copy {
+    unsigned char *dst;
+    unsigned bytes;
+    unsigned char data[16];
+};
+struct pending_list; // (std::vector in emu_runner.cpp)
 struct thread_ctx {
     int tid;
     unsigned long long bid;
     unsigned char *smem;
     void (*yield)(thread_ctx *);
+    pending_list *pend; // this thread's cp.async copies between issue and cp.async.wait_group
 };
 extern unsigned long long grid_size; // CTAs of the emulated launch (persistent kernels stride by it)
 extern int failed;                   // set by device code that would hang or trap on the GPU
@@ -79,6 +88,18 @@ template <class E> struct checked_ptr {
     E *p;
     checked_ref<E> operator[](long i) const { return checked_ref<E>{p + i}; }
 };
+#endif
+// Asynchronous copies, modelled pessimistically: at the issue the destination is POISONED (all-ones bytes: NaN for
+// both precisions) and, under the race checker, counts as written by the issuing thread -- so a thread that still
+// reads or writes the old contents in that barrier interval is a reported race; the data lands only at the wait
+// (cp.async: the issuing thread's cp.async.wait_group, after which a barrier must publish it -- the landing is a
+// write of that thread in the race checker; cp.async.bulk: the mbarrier wait every thread performs itself).  A
+// kernel that touches the destination between issue and wait computes NaNs and fails its parity test.
+void async_issue_raw(void *dst, const void *src, unsigned bytes, bool bulk);
+void async_wait_raw(bool bulk);
+template <class E> inline E *raw_ptr(E *p) { return p; }
+#ifdef BBFFT_EMU_RACECHECK
+template <class E> inline E *raw_ptr(checked_ptr<E> p) { return p.p; }
 #endif
 inline int thread_idx() { return current->tid; }
 inline unsigned long long block_idx() { return current->bid; }

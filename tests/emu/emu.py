@@ -33,13 +33,15 @@ RACECHECK = os.environ.get("BBFFT_EMU_RACECHECK", "0") == "1"
 
 def _compile(desc):
     os.makedirs(_CACHE, exist_ok=True)
-    hdr = open(os.path.join(_KERNELS, "bbfft_kernels.cuh")).read()
+    # BBFFT_EMU_KERNELS_DIR: a directory with another bbfft_kernels.cuh (the mutation tests of the emulator itself)
+    kernels = os.environ.get("BBFFT_EMU_KERNELS_DIR") or _KERNELS
+    hdr = open(os.path.join(kernels, "bbfft_kernels.cuh")).read()
     runner = open(os.path.join(_HERE, "emu_runner.cpp")).read()
     shim = open(os.path.join(_HERE, "cuda_emu.hpp")).read()
     key = hashlib.sha1((desc["source"] + hdr + runner + shim + str(RACECHECK)).encode()).hexdigest()[:20]
     so = os.path.join(_CACHE, key + ".so")
     if not os.path.exists(so):
-        stub = os.path.join(_CACHE, key + ".cpp")
+        stub = os.path.join(_CACHE, key + ".%d.cpp" % os.getpid())
         with open(stub, "w") as f:
             f.write(desc["source"])
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -47,11 +49,11 @@ def _compile(desc):
         if RACECHECK:
             extra.append("-DBBFFT_EMU_RACECHECK")
         cmd = [cxx, "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-DBBFFT_EMU"] + extra + [
-               "-DBBFFT_EMU_KERNEL=" + desc["identifier"], "-I" + _HERE, "-I" + _KERNELS, "-include",
+               "-DBBFFT_EMU_KERNEL=" + desc["identifier"], "-I" + _HERE, "-I" + kernels, "-include",
                os.path.join(_HERE, "cuda_emu.hpp"), stub, os.path.join(_HERE, "emu_runner.cpp"), "-o",
-               so + ".tmp"]
+               so + ".%d.tmp" % os.getpid()]  # (pytest-xdist workers may build the same kernel at once)
         subprocess.check_call(cmd)
-        os.replace(so + ".tmp", so)
+        os.replace(so + ".%d.tmp" % os.getpid(), so)
     return C.CDLL(so)
 
 

@@ -20,6 +20,38 @@ typedef bbk::args emu_args_t;
 extern "C" void BBFFT_EMU_KERNEL(emu_args_t a);
 
 namespace bbfft_emu {
+struct pending_list {
+    std::vector<pending_copy> v;
+};
+static pending_list bulk_pending; // cp.async.bulk copies of the running CTA (one mbarrier per kernel)
+static void push_copy(pending_list &l, void *dst, const void *src, unsigned bytes) {
+    unsigned char *d = static_cast<unsigned char *>(dst);
+    const unsigned char *s = static_cast<const unsigned char *>(src);
+    for (unsigned off = 0; off < bytes; off += 16) {
+        pending_copy c;
+        c.dst = d + off;
+        c.bytes = bytes - off < 16 ? bytes - off : 16;
+        std::memcpy(c.data, s + off, c.bytes);
+        l.v.push_back(c);
+    }
+    std::memset(dst, 0xff, bytes);
+}
+void async_issue_raw(void *dst, const void *src, unsigned bytes, bool bulk) {
+#ifdef BBFFT_EMU_RACECHECK
+    note_access(dst, bytes, true);
+#endif
+    push_copy(bulk ? bulk_pending : *current->pend, dst, src, bytes);
+}
+void async_wait_raw(bool bulk) {
+    pending_list &l = bulk ? bulk_pending : *current->pend;
+    for (auto const &c : l.v) {
+#ifdef BBFFT_EMU_RACECHECK
+        if (!bulk) note_access(c.dst, c.bytes, true);
+#endif
+        std::memcpy(c.dst, c.data, c.bytes);
+    }
+    l.v.clear();
+}
 thread_local thread_ctx *current = nullptr;
 unsigned long long grid_size = 1;
 int failed = 0;
@@ -71,6 +103,7 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
     bbfft_emu::grid_size = grid;
     bbfft_emu::failed = 0;
     std::vector<fiber> fibers(threads);
+    std::vector<bbfft_emu::pending_list> pending(threads);
     for (auto &f : fibers) {
         f.stack = static_cast<char *>(std::malloc(stack_bytes));
     }
@@ -94,6 +127,7 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
     for (unsigned long long bb = 0; bb < grid; ++bb) {
         const unsigned long long bid = reverse ? grid - 1 - bb : bb; // CTAs run in any order, too
         std::memset(smem.data(), fill, smem.size());
+        bbfft_emu::bulk_pending.v.clear();
 #ifdef BBFFT_EMU_RACECHECK
         std::fill(shadow_words.begin(), shadow_words.end(), bbfft_emu::word_state{});
 #endif
@@ -101,7 +135,8 @@ extern "C" int emu_launch(emu_args_t *a, unsigned long long grid, int threads, u
             fiber &f = fibers[t];
             f.done = false;
             f.epoch = 0;
-            f.ctx = {t, bid, smem.data(), yield_to_sched};
+            pending[t].v.clear();
+            f.ctx = {t, bid, smem.data(), yield_to_sched, &pending[t]};
             getcontext(&f.uc);
             f.uc.uc_stack.ss_sp = f.stack;
             f.uc.uc_stack.ss_size = stack_bytes;

@@ -277,6 +277,41 @@ def test_real_2d_emulated_fused_tile_kernel(pkg, fp, inplace, M, N1, N2, K):
     assert rel_l2(back, want) < TOL[fp] * 0.1
 
 
+@pytest.mark.parametrize("mutation", ["no barrier before the staging copies", "no wait for the tile copies"])
+def test_emulator_catches_async_copy_hazards(pkg, monkeypatch, tmp_path, mutation):
+    """The emulator models cp.async / cp.async.bulk pessimistically (destination poisoned from issue to wait, the
+    issue counts as a write of the issuing thread).  Two mutations of the staged tile kernel prove that the model
+    bites: without the barrier in front of the staging copies the race checker reports the threads that still
+    read the buffer; without the wait the first stage consumes poison and the result is NaN."""
+    import os
+    src = open(os.path.join(emu._KERNELS, "bbfft_kernels.cuh")).read()
+    if mutation.startswith("no barrier"):
+        old = "        BBK_SYNC(); // the tile (or the staging buffer) has left shared memory\n        after_loads();"
+        new = "        after_loads();"
+    else:
+        old = "        async_wait_all();\n        if (bulk) {\n            mbar_wait(sm, C::STG_OFF + C::STG, phase);"
+        new = "        if (bulk) {\n            mbar_wait(sm, C::STG_OFF + C::STG, phase);"
+    assert src.count(old) == 1
+    (tmp_path / "bbfft_kernels.cuh").write_text(src.replace(old, new))
+    monkeypatch.setenv("BBFFT_EMU_KERNELS_DIR", str(tmp_path))
+    monkeypatch.setattr(emu, "RACECHECK", True)
+    cfg = pkg.make_config(2, [1, 32, 32, 5], 4, -1, pkg.C2C, inplace=False)
+    rng = np.random.default_rng(5)
+    x = random_complex(rng, (32 * 32 * 5,), 4)
+    y = np.zeros_like(x)
+    if mutation.startswith("no barrier"):
+        with pytest.raises(RuntimeError, match="shared-memory race"):
+            emu.run(cfg, x, y, "SG=24", grid=2)
+    else:
+        emu.run(cfg, x, y, "SG=24", grid=2)
+        assert np.isnan(y.view(np.float32)).any()
+    # the unmutated header passes the same run
+    monkeypatch.delenv("BBFFT_EMU_KERNELS_DIR")
+    y2 = np.zeros_like(x)
+    emu.run(cfg, x, y2, "SG=24", grid=2)
+    assert not np.isnan(y2.view(np.float32)).any()
+
+
 # ---- chained nd kernel (bbk::chain): all steps of a 2d/3d plan in one persistent launch ----------
 @pytest.mark.parametrize("desc,fp,shape_np,kind,kblock,epochs", [
     ("dcfo32x32x32*3", 8, (3, 32, 32, 32, 1), "c2c", 2, 1),      # fused tile step + 1d pass
