@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--racecheck", action="store_true")
     ap.add_argument("--maxn", type=int, default=160)
     ap.add_argument("--nd", type=int, default=0, help="additional random 2d / 3d c2c configurations (tile kernel, chain)")
+    ap.add_argument("--real2d", type=int, default=0, help="additional random 2d r2c / c2r configurations (fused real tile kernels)")
     args = ap.parse_args()
     if args.racecheck:
         os.environ["BBFFT_EMU_RACECHECK"] = "1"
@@ -136,6 +137,56 @@ def main():
         ok = err < TOL[fp] * 0.5
         bad += 0 if ok else 1
         print("%s nd fp=%d M=%d N=%s K=%d dir=%d err=%.2e %s" % ("ok  " if ok else "BAD ", fp, M, Ns, K, d, err, what[:70]), flush=True)
+    # ---- real 2d: fused r2c / c2r tile kernels (even N1, default layouts, in and out of place)
+    for it in range(args.real2d):
+        fp = rnd.choice([4, 8])
+        M = rnd.choice([1, 1, 2, 3, 4])
+        N1 = rnd.choice([4, 6, 8, 10, 12, 16, 18, 20, 24, 30, 32, 36, 40, 48, 50, 64, 96, 128])
+        N2 = rnd.choice([8, 9, 12, 15, 16, 20, 24, 27, 32, 36, 48, 64, 100, 128])
+        K = rnd.randint(1, 3)
+        inplace = rnd.choice([False, True])
+        fwd = rnd.choice([True, False])
+        ns = N1 // 2 + 1
+        n1r = 2 * ns if inplace else N1
+        rdt, cdt = (np.float32, np.complex64) if fp == 4 else (np.float64, np.complex128)
+        rng = np.random.default_rng(5000 + it)
+        x = rng.uniform(-1, 1, (K, N2, N1, M)).astype(rdt)
+        spec = np.fft.fft(np.fft.rfft(x.astype(np.float64), axis=2), axis=1)
+        cfg = pkg.make_config(2, [M, N1, N2, K], fp, -1 if fwd else 1, 1 if fwd else 2, inplace=inplace)
+        try:
+            if fwd:
+                xin = np.zeros((K, N2, n1r, M), dtype=rdt)
+                xin[:, :, :N1, :] = x
+                if inplace:
+                    buf = xin.reshape(-1).copy()
+                    _, desc = emu.run(cfg, buf, None)
+                    got = buf.view(cdt).reshape(K, N2, ns, M)
+                else:
+                    got = np.zeros((K, N2, ns, M), dtype=cdt)
+                    _, desc = emu.run(cfg, xin.reshape(-1), got.reshape(-1))
+                want = spec
+            else:
+                sp = spec.astype(cdt)
+                if inplace:
+                    buf = np.zeros(K * N2 * n1r * M, dtype=rdt)
+                    buf.view(cdt)[:] = sp.reshape(-1)
+                    _, desc = emu.run(cfg, buf, None)
+                    got = buf.reshape(K, N2, n1r, M)[:, :, :N1, :]
+                else:
+                    got = np.zeros((K, N2, N1, M), dtype=rdt)
+                    _, desc = emu.run(cfg, sp.reshape(-1).copy(), got.reshape(-1))
+                want = x.astype(np.float64) * (N1 * N2)
+        except pkg.BadConfiguration:
+            continue  # not a single fused kernel (tile too small or too large): one launch per mode, covered by the 1d runs
+        except Exception as ex:
+            print("FAILED to run real 2d:", fp, M, N1, N2, K, str(ex)[:160])
+            bad += 1
+            continue
+        err = rel_l2(got, want)
+        ok = err < TOL[fp] * 0.5
+        bad += 0 if ok else 1
+        print("%s real2d %s fp=%d M=%d N=%dx%d K=%d inplace=%d err=%.2e %s" % (
+            "ok  " if ok else "BAD ", "r2c" if fwd else "c2r", fp, M, N1, N2, K, inplace, err, desc["identifier"][:70]), flush=True)
     print("done: %d problems" % bad)
     return 1 if bad else 0
 
