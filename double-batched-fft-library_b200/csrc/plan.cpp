@@ -691,7 +691,10 @@ unsigned nd_plan::launches_per_execute() const {
 void nd_plan::enqueue(void const *in, void *out, cudaStream_t stream) {
     if (real_tile_ && !real_tile_->pointers_ok(in, out)) {
         // the user's real tensor is not aligned to a complex number: one launch per mode handles any pointer
-        if (!unfused_) unfused_ = std::make_unique<nd_plan>(cfg_, api_, cache_, false);
+        {
+            std::lock_guard<std::mutex> lock(unfused_mtx_);
+            if (!unfused_) unfused_ = std::make_unique<nd_plan>(cfg_, api_, cache_, false);
+        }
         unfused_->enqueue(in, out, stream);
         return;
     }

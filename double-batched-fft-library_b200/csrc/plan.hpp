@@ -177,6 +177,7 @@ class nd_plan : public plan_base {
     jit_cache *cache_ = nullptr;
     std::shared_ptr<fft2d_plan> real_tile_;
     std::unique_ptr<nd_plan> unfused_;
+    std::mutex unfused_mtx_; // (executes of one plan may come from several host threads)
     // chained execution: all steps in one persistent launch (bbk::chain)
     bool try_chain(std::vector<nd_step> const &steps, jit_cache *cache);
     bool chained_ = false;
