@@ -19,8 +19,8 @@ def test_seeded_fuzz_of_fused_real_2d_kernels(pkg):
     """Random r2c / c2r 2d configurations (precision, M, N1 x N2, K, placement) through the fused real tile kernels
     under the emulator's race checker, judged by numpy's float64 rfft2 / irfft2."""
     env = dict(os.environ, BBFFT_EMU_RACECHECK="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_emu.py"), "--n", "0", "--real2d", "60", "--seed", "5"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_emu.py"), "--n", "0", "--real2d", "45", "--seed", "5"],
                        capture_output=True, text=True, timeout=1500, env=env)
     tail = "\n".join(r.stdout.splitlines()[-40:])
     assert r.returncode == 0 and "done: 0 problems" in r.stdout, tail + r.stderr[-2000:]
-    assert r.stdout.count("ok   real2d") >= 10, tail
+    assert r.stdout.count("ok   real2d") >= 8, tail

@@ -202,12 +202,11 @@ def test_c2c_2d_emulated_tile_kernel_vs_oracle(pkg, oracle, fp, M, N1, N2, K, tu
     assert np.array_equal(z, y)
 
 
-@pytest.mark.parametrize("fp", [4, 8])
-@pytest.mark.parametrize("M,N1,N2,K,tune,grid", [
-    (1, 32, 32, 5, "SG=24", 2), (1, 32, 32, 5, "SG=-1", 2), (1, 64, 64, 3, "SG=48", 1), (1, 40, 30, 4, "SG=7", 3),
-    (16, 8, 8, 3, "SG=2", 2), (3, 20, 18, 3, "SG=10", 1), (1, 16, 128, 2, "RA=16,RB=2x8x8,SG=100", 1),
-    (1, 128, 16, 3, "SG=1,PS=1", 2), (1, 32, 32, 4, "PS=1", 3), (2, 25, 49, 2, "TH=128,SG=48", 1),
-    (1, 32, 32, 5, "SG=-1,BK=1", 2), (1, 40, 30, 4, "SG=7,BK=1", 3),
+@pytest.mark.parametrize("fp,M,N1,N2,K,tune,grid", [
+    (4, 1, 32, 32, 5, "SG=24", 2), (8, 1, 32, 32, 5, "SG=-1", 2), (4, 1, 64, 64, 3, "SG=48", 1), (8, 1, 40, 30, 4, "SG=7", 3),
+    (4, 16, 8, 8, 3, "SG=2", 2), (8, 3, 20, 18, 3, "SG=10", 1), (4, 1, 16, 128, 2, "RA=16,RB=2x8x8,SG=100", 1),
+    (8, 1, 128, 16, 3, "SG=1,PS=1", 2), (4, 1, 32, 32, 4, "PS=1", 3), (8, 2, 25, 49, 2, "TH=128,SG=48", 1),
+    (4, 1, 32, 32, 5, "SG=-1,BK=1", 2), (8, 1, 32, 32, 5, "SG=-1,BK=1", 2), (4, 1, 40, 30, 4, "SG=7,BK=1", 3),
 ])
 def test_c2c_2d_emulated_staged_tile_kernel(pkg, oracle, fp, M, N1, N2, K, tune, grid):
     """The persistent tile kernels (asynchronous pipeline, PS=1; staging buffer for the leading rows of the
@@ -234,10 +233,10 @@ def test_c2c_2d_emulated_staged_tile_kernel(pkg, oracle, fp, M, N1, N2, K, tune,
     assert np.array_equal(z, y)
 
 
-@pytest.mark.parametrize("fp", [4, 8])
-@pytest.mark.parametrize("inplace", [False, True])
-@pytest.mark.parametrize("M,N1,N2,K", [(1, 64, 32, 2), (1, 32, 64, 1), (3, 20, 36, 2), (2, 12, 160, 1), (16, 8, 16, 2),
-                                       (1, 128, 16, 1), (1, 40, 60, 2), (1, 6, 400, 1), (1, 4, 512, 1)])
+@pytest.mark.parametrize("fp,inplace,M,N1,N2,K", [
+    (4, False, 1, 64, 32, 2), (8, True, 1, 64, 32, 2), (4, True, 1, 32, 64, 1), (8, False, 3, 20, 36, 2), (4, True, 3, 20, 36, 2),
+    (4, False, 2, 12, 160, 1), (8, True, 16, 8, 16, 2), (4, False, 16, 8, 16, 2), (4, False, 1, 128, 16, 1), (8, True, 1, 128, 16, 1),
+    (8, False, 1, 40, 60, 2), (4, True, 1, 40, 60, 2), (4, False, 1, 6, 400, 1), (8, True, 1, 4, 512, 1), (4, False, 1, 4, 512, 1)])
 def test_real_2d_emulated_fused_tile_kernel(pkg, fp, inplace, M, N1, N2, K):
     """The fused real tile kernels (bbk::fft2d_tile_real_cta): r2c = half-length pass along n1 from the real rows,
     split on the pairs (i, N1/2 - i), column pass; c2r = the mirror image.  Against numpy's rfft2 / irfft2 in
